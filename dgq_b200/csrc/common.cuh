@@ -1,0 +1,71 @@
+// Shared host/device helpers for the dgq_b200 kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dgq_b200.h"
+
+#define DGQ_CHECK_ARG(cond)                    \
+  do {                                         \
+    if (!(cond)) return DGQ_ERR_INVALID_VALUE; \
+  } while (0)
+
+#define DGQ_RETURN_LAST_ERROR()                    \
+  do {                                             \
+    cudaError_t e__ = cudaGetLastError();          \
+    return e__ == cudaSuccess ? 0 : static_cast<int>(e__); \
+  } while (0)
+
+namespace dgq {
+
+constexpr int kNumSMs = 148;
+
+// quantize one value exactly as UniformAffineQuantizer does (quant/quant_layer.py:295-299):
+// IEEE division, round-half-to-even, clamp to [0, level-1].  Returns the integer code as float.
+__device__ __forceinline__ float uaq_code(float x, float delta, float zp, float qmax) {
+  float q = rintf(__fdiv_rn(x, delta)) + zp;
+  return fminf(fmaxf(q, 0.0f), qmax);
+}
+__device__ __forceinline__ float uaq_dequant(float code, float delta, float zp) {
+  return __fmul_rn(delta, __fsub_rn(code, zp));
+}
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// exact-erf GELU (torch.nn.functional.gelu default)
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+union Half8 {
+  uint4 u;
+  __half2 h2[4];
+  __half h[8];
+};
+
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  Half8 t;
+  t.u = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(t.h2[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  Half8 t;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t.h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  return t.u;
+}
+
+}  // namespace dgq

@@ -1,0 +1,572 @@
+// A-operand producers: everything between two GEMMs of the quantized UNet, fused with the
+// activation quantizer of the consuming QuantLayer.  All are HBM-bound, 16-byte vectorised,
+// one pass over their input (taps of a 3x3 window re-read through L1/L2).
+//
+//   dgq_act_producer  [concat] -> [nearest x2] -> [GroupNorm] -> [SiLU] -> im2col -> quantize
+//   dgq_gn_stats      GroupNorm(32) mean / rstd (deterministic two-stage reduction)
+//   dgq_ln_quant      LayerNorm + up to 3 quantizers
+//   dgq_row_quant     quantizer only (fp32 or fp16 rows)
+//   dgq_geglu_quant   x1 * gelu(x2) + quantizer
+//   dgq_qkv_pack      head split (+transpose for V) + quantizer -> attention operands
+//
+// Reference semantics: quant/quant_layer.py:295-299 (quantizer), :630-641 (unfold then quantize:
+// zero padding IS quantised on that path), quant/quant_block.py:98-119.
+#include "common.cuh"
+
+namespace dgq {
+
+struct QuantDev {
+  const float* delta;
+  const float* zp;
+  int mode;
+  int period;
+  float qmax;
+};
+
+static QuantDev to_dev(const dgq_quant_t& q) { return QuantDev{q.delta, q.zp, q.mode, q.period, q.qmax}; }
+
+// quantize 8 consecutive K positions k0..k0+7 of row `row`; returns de-quantised values in v
+__device__ __forceinline__ void quant8(const QuantDev& q, float (&v)[8], int k0, int row, uint8_t* codes8) {
+  if (q.mode == DGQ_Q_NONE) return;
+  float d[8], z[8];
+  if (q.mode == DGQ_Q_KWISE) {
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(q.delta + k0));
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(q.delta + k0 + 4));
+    const float4 z0 = __ldg(reinterpret_cast<const float4*>(q.zp + k0));
+    const float4 z1 = __ldg(reinterpret_cast<const float4*>(q.zp + k0 + 4));
+    d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+    z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+  } else {
+    const int j = q.mode == DGQ_Q_ROWWISE ? row % q.period : 0;
+    const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; }
+  }
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float c = uaq_code(v[i], d[i], z[i], q.qmax);
+    v[i] = uaq_dequant(c, d[i], z[i]);
+    if (i < 4) lo |= static_cast<uint32_t>(c) << (8 * i);
+    else hi |= static_cast<uint32_t>(c) << (8 * (i - 4));
+  }
+  if (codes8 != nullptr) *reinterpret_cast<uint2*>(codes8) = make_uint2(lo, hi);
+}
+
+// ------------------------------------------------------------------------------------------
+struct ProducerDev {
+  const void* src0;
+  const void* src1;
+  int c0, c1;
+  int batch, h, w, hs, ws, ho, wo;
+  int upsample, ksize, stride, pad;
+  const float* gn_mean;
+  const float* gn_rstd;
+  const float* gn_gamma;
+  const float* gn_beta;
+  int act;
+  QuantDev q;
+  int pad_quantized;
+  __half* out;
+  int ldo;
+  uint8_t* codes;
+};
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) {
+  const int C = p.c0 + p.c1;
+  const int K = p.ksize * p.ksize * C;
+  const int kvec = p.ldo >> 3;
+  const int64_t total = static_cast<int64_t>(p.batch) * p.ho * p.wo * kvec;
+  const int cpg = C >> 5;  // channels per GroupNorm group
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(idx / kvec);
+    const int k0 = static_cast<int>(idx % kvec) << 3;
+    __half* dst = p.out + static_cast<size_t>(m) * p.ldo + k0;
+    if (k0 >= K) {  // zero padding of the K tail (ldo > K)
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    const int tap = k0 / C, c = k0 % C;
+    const int ox = m % p.wo;
+    const int oy = (m / p.wo) % p.ho;
+    const int b = m / (p.wo * p.ho);
+    const int iy = oy * p.stride - p.pad + tap / p.ksize;
+    const int ix = ox * p.stride - p.pad + tap % p.ksize;
+    float v[8];
+    const bool inside = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+    if (inside) {
+      const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+      const size_t pix = (static_cast<size_t>(b) * p.hs + sy) * p.ws + sx;
+      if (c < p.c0) load8(static_cast<const TIn*>(p.src0) + pix * p.c0 + c, v);
+      else load8(static_cast<const TIn*>(p.src1) + pix * p.c1 + (c - p.c0), v);
+      if (p.gn_mean != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int g = (c + i) / cpg;
+          const float mean = __ldg(p.gn_mean + b * 32 + g), rstd = __ldg(p.gn_rstd + b * 32 + g);
+          v[i] = (v[i] - mean) * rstd * __ldg(p.gn_gamma + c + i) + __ldg(p.gn_beta + c + i);
+        }
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+    }
+    uint8_t* cdst = p.codes != nullptr ? p.codes + static_cast<size_t>(m) * K + k0 : nullptr;
+    if (inside || p.pad_quantized) quant8(p.q, v, k0, m, cdst);
+    else if (cdst != nullptr) *reinterpret_cast<uint2*>(cdst) = make_uint2(0, 0);
+    *reinterpret_cast<uint4*>(dst) = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GroupNorm statistics, stage 1: CTA (b, chunk) sums rows [chunk*rows_per, ...) per channel, folds
+// channels into the 32 groups, writes partial (sum, sumsq) to scratch[b][chunk][32][2].
+constexpr int kGnMaxC = 2560;
+__global__ void __launch_bounds__(256) gn_partial_kernel(const __half* __restrict__ src0,
+                                                         const __half* __restrict__ src1, int c0, int c1, int hw,
+                                                         int rows_per, int chunks, float* __restrict__ scratch) {
+  const int C = c0 + c1;
+  const int cpg = C >> 5;
+  const int b = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int r0 = chunk * rows_per;
+  const int r1 = min(hw, r0 + rows_per);
+  // per-(row-lane, channel) partial sums; reduced in a fixed order below (deterministic)
+  __shared__ float s_sum[kGnMaxC], s_sq[kGnMaxC];
+  const int cvec = C >> 3;
+  const int tid = threadIdx.x;
+  int cv0, sub, nsub, cstep;
+  if (cvec >= static_cast<int>(blockDim.x)) { cv0 = tid; sub = 0; nsub = 1; cstep = blockDim.x; }
+  else { nsub = blockDim.x / cvec; cv0 = tid % cvec; sub = tid / cvec; cstep = cvec; if (sub >= nsub) cv0 = cvec; }
+  for (int cv = cv0; cv < cvec; cv += cstep) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    const int c = cv << 3;
+    for (int r = r0 + sub; r < r1; r += nsub) {
+      const size_t pix = static_cast<size_t>(b) * hw + r;
+      float v[8];
+      if (c < c0) load8(src0 + pix * c0 + c, v);
+      else load8(src1 + pix * c1 + (c - c0), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s_sum[sub * C + c + i] = s[i]; s_sq[sub * C + c + i] = q[i]; }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f, q = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c)
+      for (int u = 0; u < nsub; ++u) { s += s_sum[u * C + c]; q += s_sq[u * C + c]; }
+    float* o = scratch + ((static_cast<size_t>(b) * chunks + chunk) * 32 + tid) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+__global__ void gn_final_kernel(const float* __restrict__ scratch, int chunks, double count, float eps,
+                                float* __restrict__ mean, float* __restrict__ rstd, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (b, g)
+  if (i >= total) return;
+  const int b = i >> 5, g = i & 31;
+  double s = 0.0, q = 0.0;
+  for (int ch = 0; ch < chunks; ++ch) {
+    const float* o = scratch + ((static_cast<size_t>(b) * chunks + ch) * 32 + g) * 2;
+    s += o[0];
+    q += o[1];
+  }
+  const double mu = s / count;
+  double var = q / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[i] = static_cast<float>(mu);
+  rstd[i] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm / plain rows + up to 3 quantizers.  One warp per row; row cached in registers.
+struct RowQuantDev {
+  QuantDev q[3];
+  __half* out[3];
+  uint8_t* codes[3];
+  int n_out;
+};
+constexpr int kMaxVecPerLane = 8;  // supports C <= 8*8*32 = 2048
+
+template <typename TIn, bool kNorm>
+__global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ x, int m, int c,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        const RowQuantDev rq) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  const int cvec = c >> 3;
+  float v[kMaxVecPerLane][8];
+  const TIn* row = x + static_cast<size_t>(warp) * c;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVecPerLane; ++j) {
+    const int cv = lane + j * 32;
+    if (cv < cvec) {
+      load8(row + (cv << 3), v[j]);
+      if (kNorm) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += v[j][i];
+      }
+    }
+  }
+  if (kNorm) {
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / static_cast<float>(c);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxVecPerLane; ++j) {
+      if (lane + j * 32 < cvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; sq += d * d; }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = 1.0f / sqrtf(sq / static_cast<float>(c) + eps);
+#pragma unroll
+    for (int j = 0; j < kMaxVecPerLane; ++j) {
+      const int cv = lane + j * 32;
+      if (cv < cvec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int cc = (cv << 3) + i;
+          v[j][i] = (v[j][i] - mean) * rstd * __ldg(gamma + cc) + __ldg(beta + cc);
+        }
+      }
+    }
+  }
+  for (int o = 0; o < rq.n_out; ++o) {
+#pragma unroll
+    for (int j = 0; j < kMaxVecPerLane; ++j) {
+      const int cv = lane + j * 32;
+      if (cv < cvec) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = v[j][i];
+        uint8_t* cd = rq.codes[o] != nullptr ? rq.codes[o] + static_cast<size_t>(warp) * c + (cv << 3) : nullptr;
+        quant8(rq.q[o], t, cv << 3, warp, cd);
+        *reinterpret_cast<uint4*>(rq.out[o] + static_cast<size_t>(warp) * c + (cv << 3)) = pack8(t);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geglu_quant_kernel(const __half* __restrict__ x, int m, int f,
+                                                          const QuantDev q, __half* __restrict__ out) {
+  const int fvec = f >> 3;
+  const int64_t total = static_cast<int64_t>(m) * fvec;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(idx / fvec);
+    const int k0 = static_cast<int>(idx % fvec) << 3;
+    float a[8], g[8];
+    load8(x + static_cast<size_t>(row) * 2 * f + k0, a);
+    load8(x + static_cast<size_t>(row) * 2 * f + f + k0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = a[i] * gelu_erf_f(g[i]);
+    quant8(q, a, k0, row, nullptr);
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * f + k0) = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// x [b*t, ldx] (head h = columns h*d..) -> out [b, heads, t, dp] (transpose == 0)
+//                                        or out [b, heads, dp, tp] (transpose == 1)
+__global__ void __launch_bounds__(256) qkv_pack_kernel(const __half* __restrict__ x, int ldx, int b, int t,
+                                                       int heads, int d, int dp, int tp, int transpose,
+                                                       int skip_first, const QuantDev q, __half* __restrict__ out) {
+  if (!transpose) {
+    const int dvec = dp >> 3;
+    const int64_t total = static_cast<int64_t>(b) * heads * t * dvec;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      const int d0 = static_cast<int>(idx % dvec) << 3;
+      int64_t r = idx / dvec;
+      const int tt = static_cast<int>(r % t); r /= t;
+      const int hh = static_cast<int>(r % heads);
+      const int bb = static_cast<int>(r / heads);
+      float v[8];
+      if (d0 < d) {
+        load8(x + (static_cast<size_t>(bb) * t + tt) * ldx + hh * d + d0, v);
+        if (!(skip_first && tt == 0)) {
+          // KWISE index = d, ROWWISE index = token (minus the bypassed start token)
+          QuantDev qq = q;
+          if (qq.mode == DGQ_Q_ROWWISE) qq.period = 1 << 30;
+          quant8(qq, v, d0, tt - skip_first, nullptr);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(bb) * heads + hh) * t + tt) * dp + d0) = pack8(v);
+    }
+  } else {
+    const int tvec = tp >> 3;
+    const int64_t total = static_cast<int64_t>(b) * heads * dp * tvec;
+    for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      // dd fastest so that a warp reads consecutive channels of the same token rows
+      const int dd = static_cast<int>(idx % dp);
+      int64_t r = idx / dp;
+      const int t0 = static_cast<int>(r % tvec) << 3; r /= tvec;
+      const int hh = static_cast<int>(r % heads);
+      const int bb = static_cast<int>(r / heads);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tt = t0 + i;
+        float val = 0.f;
+        if (dd < d && tt < t) {
+          val = __half2float(x[(static_cast<size_t>(bb) * t + tt) * ldx + hh * d + dd]);
+          if (q.mode != DGQ_Q_NONE && !(skip_first && tt == 0)) {
+            const int j = q.mode == DGQ_Q_KWISE ? dd : (q.mode == DGQ_Q_ROWWISE ? tt - skip_first : 0);
+            const float dl = __ldg(q.delta + j), z = __ldg(q.zp + j);
+            val = uaq_dequant(uaq_code(val, dl, z, q.qmax), dl, z);
+          }
+        }
+        v[i] = val;
+      }
+      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(bb) * heads + hh) * dp + dd) * tp + t0) = pack8(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, __half* __restrict__ o16,
+                                          float* __restrict__ o32, int ldo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim >> 1;
+  if (i >= n * half) return;
+  const int r = i / half, j = i % half;
+  // exponent = -ln(10000) * j / half   (diffusers_rewrite/sd.py:27-31)
+  const float e = expf(-9.210340371976184f * static_cast<float>(j) / static_cast<float>(half));
+  const float a = t[r] * e;
+  const float cs = cosf(a), sn = sinf(a);
+  if (o16 != nullptr) {
+    o16[static_cast<size_t>(r) * ldo + j] = __float2half_rn(cs);
+    o16[static_cast<size_t>(r) * ldo + half + j] = __float2half_rn(sn);
+  }
+  if (o32 != nullptr) {
+    o32[static_cast<size_t>(r) * ldo + j] = cs;
+    o32[static_cast<size_t>(r) * ldo + half + j] = sn;
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int b, int c, int hw, int c_pad,
+                                    __half* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(b) * hw * c_pad;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c_pad);
+    const int64_t r = i / c_pad;
+    const int p = static_cast<int>(r % hw);
+    const int bb = static_cast<int>(r / hw);
+    out[i] = cc < c ? __float2half_rn(x[(static_cast<size_t>(bb) * c + cc) * hw + p]) : __float2half_rn(0.f);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int b, int c, int hw, int ldx,
+                                    float* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(b) * c * hw;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i % hw);
+    const int64_t r = i / hw;
+    const int cc = static_cast<int>(r % c);
+    const int bb = static_cast<int>(r / c);
+    out[i] = __half2float(x[(static_cast<size_t>(bb) * hw + p) * ldx + cc]);
+  }
+}
+__global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(silu_f(__half2float(x[i])));
+}
+__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, int64_t n,
+                           __half* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = __float2half_rn(__half2float(a[i]) + __half2float(b[i]));
+}
+
+static int grid_for(int64_t work, int block, int max_blocks) {
+  int64_t g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  return static_cast<int>(g < max_blocks ? g : max_blocks);
+}
+static bool quant_ok(const dgq_quant_t& q) {
+  if (q.mode == DGQ_Q_NONE) return true;
+  if (q.mode < 0 || q.mode > DGQ_Q_ROWWISE) return false;
+  if (q.delta == nullptr || q.zp == nullptr) return false;
+  if (q.mode == DGQ_Q_ROWWISE && q.period <= 0) return false;
+  return true;
+}
+
+}  // namespace dgq
+
+extern "C" int dgq_act_producer(const dgq_producer_t* a, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(a != nullptr && a->src0 != nullptr && a->out != nullptr);
+  DGQ_CHECK_ARG(a->c0 > 0 && a->c0 % 8 == 0 && a->c1 >= 0 && a->c1 % 8 == 0);
+  DGQ_CHECK_ARG(a->c1 == 0 || a->src1 != nullptr);
+  DGQ_CHECK_ARG(a->batch > 0 && a->h > 0 && a->w > 0);
+  DGQ_CHECK_ARG((a->ksize == 1 && a->pad == 0) || (a->ksize == 3 && a->pad == 1));
+  DGQ_CHECK_ARG(a->stride == 1 || a->stride == 2);
+  DGQ_CHECK_ARG(!a->upsample || (a->h % 2 == 0 && a->w % 2 == 0));
+  DGQ_CHECK_ARG(quant_ok(a->q));
+  const int C = a->c0 + a->c1;
+  const int K = a->ksize * a->ksize * C;
+  DGQ_CHECK_ARG(a->ldo >= K && a->ldo % 8 == 0);
+  DGQ_CHECK_ARG(a->gn_mean == nullptr ||
+                (a->gn_rstd != nullptr && a->gn_gamma != nullptr && a->gn_beta != nullptr && C % 32 == 0));
+  ProducerDev p;
+  p.src0 = a->src0; p.src1 = a->src1; p.c0 = a->c0; p.c1 = a->c1;
+  p.batch = a->batch; p.h = a->h; p.w = a->w;
+  p.hs = a->upsample ? a->h / 2 : a->h; p.ws = a->upsample ? a->w / 2 : a->w;
+  p.ho = (a->h + 2 * a->pad - a->ksize) / a->stride + 1;
+  p.wo = (a->w + 2 * a->pad - a->ksize) / a->stride + 1;
+  p.upsample = a->upsample; p.ksize = a->ksize; p.stride = a->stride; p.pad = a->pad;
+  p.gn_mean = a->gn_mean; p.gn_rstd = a->gn_rstd; p.gn_gamma = a->gn_gamma; p.gn_beta = a->gn_beta;
+  p.act = a->act; p.q = to_dev(a->q); p.pad_quantized = a->pad_quantized;
+  p.out = static_cast<__half*>(a->out); p.ldo = a->ldo; p.codes = a->codes;
+  const int64_t total = static_cast<int64_t>(p.batch) * p.ho * p.wo * (p.ldo / 8);
+  const int grid = grid_for(total, 256, kNumSMs * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->src_is_f32) act_producer_kernel<float><<<grid, 256, 0, s>>>(p);
+  else act_producer_kernel<__half><<<grid, 256, 0, s>>>(p);
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_gn_stats(const void* src0, const void* src1, int c0, int c1, int batch, int hw, float eps,
+                            float* mean, float* rstd, float* scratch, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(src0 != nullptr && mean != nullptr && rstd != nullptr && scratch != nullptr);
+  DGQ_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 && (c0 + c1) % 32 == 0);
+  DGQ_CHECK_ARG(c1 == 0 || src1 != nullptr);
+  DGQ_CHECK_ARG(batch > 0 && hw > 0 && (c0 + c1) <= kGnMaxC);
+  int chunks = (hw + 63) / 64;
+  if (chunks > 64) chunks = 64;
+  const int rows_per = (hw + chunks - 1) / chunks;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  gn_partial_kernel<<<batch * chunks, 256, 0, s>>>(static_cast<const __half*>(src0),
+                                                   static_cast<const __half*>(src1), c0, c1, hw, rows_per, chunks,
+                                                   scratch);
+  const double count = static_cast<double>(hw) * ((c0 + c1) / 32);
+  gn_final_kernel<<<(batch * 32 + 127) / 128, 128, 0, s>>>(scratch, chunks, count, eps, mean, rstd, batch * 32);
+  DGQ_RETURN_LAST_ERROR();
+}
+
+static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int c, const float* gamma,
+                            const float* beta, float eps, int n_out, const dgq_quant_t* q, void* const* out,
+                            uint8_t* const* codes, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && m > 0 && c > 0 && c % 8 == 0 && c <= kMaxVecPerLane * 256);
+  DGQ_CHECK_ARG(n_out >= 1 && n_out <= 3 && q != nullptr && out != nullptr);
+  RowQuantDev rq;
+  rq.n_out = n_out;
+  for (int i = 0; i < 3; ++i) {
+    rq.out[i] = nullptr; rq.codes[i] = nullptr;
+    rq.q[i] = QuantDev{nullptr, nullptr, DGQ_Q_NONE, 1, 0.f};
+  }
+  for (int i = 0; i < n_out; ++i) {
+    DGQ_CHECK_ARG(out[i] != nullptr && quant_ok(q[i]));
+    rq.q[i] = to_dev(q[i]);
+    rq.out[i] = static_cast<__half*>(out[i]);
+    rq.codes[i] = codes != nullptr ? codes[i] : nullptr;
+  }
+  const int grid = (m + 7) / 8;  // 8 warps (rows) per CTA
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (norm) {
+    DGQ_CHECK_ARG(gamma != nullptr && beta != nullptr && !src_is_f32);
+    row_quant_kernel<__half, true><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, gamma, beta, eps, rq);
+  } else if (src_is_f32) {
+    row_quant_kernel<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, nullptr, nullptr, 0.f, rq);
+  } else {
+    row_quant_kernel<__half, false><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, nullptr, nullptr, 0.f, rq);
+  }
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_ln_quant(const void* x, int m, int c, const float* gamma, const float* beta, float eps,
+                            int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream) {
+  return launch_row_quant(x, 0, true, m, c, gamma, beta, eps, n_out, host_q, host_out, nullptr, stream);
+}
+extern "C" int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_out, const dgq_quant_t* host_q,
+                             void* const* host_out, uint8_t* const* host_codes, void* stream) {
+  return launch_row_quant(x, src_is_f32, false, m, c, nullptr, nullptr, 0.f, n_out, host_q, host_out, host_codes,
+                          stream);
+}
+
+extern "C" int dgq_geglu_quant(const void* x, int m, int f, dgq_quant_t q, void* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && out != nullptr && m > 0 && f > 0 && f % 8 == 0 && quant_ok(q));
+  const int64_t total = static_cast<int64_t>(m) * (f / 8);
+  geglu_quant_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), m, f, to_dev(q), static_cast<__half*>(out));
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_qkv_pack(const void* x, int ldx, int b, int t, int heads, int d, int dp, int tp, int transpose,
+                            int skip_first, dgq_quant_t q, void* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && t > 0 && heads > 0 && d > 0);
+  DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && quant_ok(q));
+  DGQ_CHECK_ARG(!transpose || (tp >= t && tp % 8 == 0));
+  const int64_t total = transpose ? static_cast<int64_t>(b) * heads * dp * (tp / 8)
+                                  : static_cast<int64_t>(b) * heads * t * (dp / 8);
+  qkv_pack_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), ldx, b, t, heads, d, dp, tp, transpose, skip_first, to_dev(q),
+      static_cast<__half*>(out));
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_timestep_embedding(const float* t, int n, int dim, void* out_f16, float* out_f32, int ldo,
+                                      void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(t != nullptr && n > 0 && dim > 0 && dim % 2 == 0 && ldo >= dim);
+  DGQ_CHECK_ARG(out_f16 != nullptr || out_f32 != nullptr);
+  const int total = n * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, n, dim, static_cast<__half*>(out_f16), out_f32, ldo);
+  DGQ_RETURN_LAST_ERROR();
+}
+extern "C" int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && c > 0 && hw > 0 && c_pad >= c);
+  const int64_t total = static_cast<int64_t>(b) * hw * c_pad;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, b, c, hw, c_pad, static_cast<__half*>(out));
+  DGQ_RETURN_LAST_ERROR();
+}
+extern "C" int dgq_nhwc_to_nchw(const void* x, int b, int c, int hw, int ldx, float* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && c > 0 && hw > 0 && ldx >= c);
+  const int64_t total = static_cast<int64_t>(b) * hw * c;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), b, c, hw, ldx, out);
+  DGQ_RETURN_LAST_ERROR();
+}
+extern "C" int dgq_silu_f16(const void* x, int64_t n, void* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(x != nullptr && out != nullptr && n > 0);
+  silu_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), n, static_cast<__half*>(out));
+  DGQ_RETURN_LAST_ERROR();
+}
+extern "C" int dgq_add_f16(const void* a, const void* b, int64_t n, void* out, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(a != nullptr && b != nullptr && out != nullptr && n > 0);
+  add_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), static_cast<const __half*>(b), n, static_cast<__half*>(out));
+  DGQ_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,284 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dgq_b200.h).
+
+torch is used for device memory and streams only; every computation below is one of the
+hand-written sm_100a kernels in dgq_b200/csrc.  Launches go to torch's current CUDA stream, so
+they are CUDA-graph capturable.  A module-level launch counter feeds bench.py's `gpu_launches`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE, MAP_NONE, MAP_UNIFORM, MAP_LOG2  # noqa: F401
+
+LAUNCHES = 0  # kernels launched through this module (some entry points launch two)
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+@dataclass
+class QParam:
+    """A (delta, zero_point) pair resident on the device plus how it is indexed."""
+    mode: int = Q_NONE
+    delta: Optional[torch.Tensor] = None
+    zp: Optional[torch.Tensor] = None
+    period: int = 1
+    qmax: float = 255.0
+
+    def struct(self) -> L.QuantT:
+        return L.QuantT(_p(self.delta), _p(self.zp), self.mode, self.period, self.qmax)
+
+
+NOQ = QParam()
+
+
+def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device, *, kperm=None) -> QParam:
+    """Map a checkpoint (delta, zp) of shape (), (1,1,X) or (1,X,1) to a device QParam
+    (SURVEY.md 8a').  `kperm` re-orders a K-wise table into the GEMM's K order (conv: tap-major)."""
+    d, z = _f32(delta, device), _f32(zp, device)
+    if d.dim() == 0 or d.numel() == 1 and d.dim() <= 1:
+        return QParam(Q_SCALAR, d.reshape(1), z.reshape(1).expand(1).contiguous(), 1, qmax)
+    if d.dim() == 3 and d.shape[0] == 1 and d.shape[1] == 1:      # (1,1,X): last axis
+        mode = Q_KWISE
+    elif d.dim() == 3 and d.shape[0] == 1 and d.shape[2] == 1:    # (1,X,1): middle axis
+        mode = Q_ROWWISE
+    else:
+        raise ValueError(f"unsupported quantizer parameter shape {tuple(d.shape)}")
+    d, z = d.reshape(-1), z.reshape(-1).expand(d.numel())
+    if kperm is not None and mode == Q_KWISE:
+        d, z = d[kperm], z[kperm]
+    return QParam(mode, d.contiguous(), z.contiguous(), d.numel(), qmax)
+
+
+# ------------------------------------------------------------------------------------------
+def fake_quant(x: torch.Tensor, delta: torch.Tensor, zp: torch.Tensor, period: int, inner: int, qmax: float,
+               want_codes: bool = False):
+    """UniformAffineQuantizer.forward on an fp32 tensor; index = (i // inner) % period."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    L.check(L.lib().dgq_fake_quant_f32(_p(x), x.numel(), _p(delta), _p(zp), period, inner, qmax, _p(out),
+                                       _p(codes), _stream()), "dgq_fake_quant_f32")
+    _count()
+    return (out, codes) if want_codes else out
+
+
+def max_f32(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(1024, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dgq_max_f32(_p(x), x.numel(), _p(out), _p(scratch), _stream()), "dgq_max_f32")
+    _count(2)
+    return out
+
+
+def t2i_log_quant(x: torch.Tensor, delta: Optional[torch.Tensor], qmax: float, want_codes: bool = False):
+    """T2ILogQuantizer.forward; delta None => real-time (x.max())."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    d = max_f32(x) if delta is None else delta
+    out = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    L.check(L.lib().dgq_t2i_log_quant_f32(_p(x), x.numel(), _p(d), qmax, _p(out), _p(codes), _stream()),
+            "dgq_t2i_log_quant_f32")
+    _count()
+    return (out, codes) if want_codes else out
+
+
+def pack_weight(w: torch.Tensor, delta, zp, alpha, qmax: float, use_wq: bool, *, ci_pad: Optional[int] = None,
+                n_pad: Optional[int] = None, want_codes: bool = False, want_packed4: bool = False):
+    """w fp32 [n, ci, kh, kw] or [n, k] -> fp16 operand [n_pad, taps*ci_pad] (K order tap-major)."""
+    assert w.is_cuda and w.dtype == torch.float32
+    w = w.contiguous()
+    n, ci = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel() if w.dim() == 4 else 1
+    ci_pad = ci_pad or (ci + 7) // 8 * 8
+    n_pad = n_pad or (n + 7) // 8 * 8
+    k_out = taps * ci_pad
+    operand = torch.empty(n_pad, k_out, dtype=torch.float16, device=w.device)
+    codes = torch.empty(n_pad, k_out, dtype=torch.uint8, device=w.device) if (want_codes or want_packed4) else None
+    packed = torch.empty(n_pad, k_out // 2, dtype=torch.uint8, device=w.device) if want_packed4 else None
+    d = _f32(delta, w.device).reshape(-1) if delta is not None else None
+    z = _f32(zp, w.device).reshape(-1) if zp is not None else None
+    if z is not None and z.numel() == 1 and n > 1:
+        z = z.expand(n).contiguous()
+    a = _f32(alpha, w.device) if alpha is not None else None
+    L.check(L.lib().dgq_pack_weight(_p(w), _p(d), _p(z), _p(a), n, ci, taps, ci_pad, n_pad, qmax, int(use_wq),
+                                    _p(codes), _p(packed), _p(operand), _stream()), "dgq_pack_weight")
+    _count(2 if want_packed4 else 1)
+    return operand, codes, packed
+
+
+def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Optional[torch.Tensor] = None,
+                 upsample: bool = False, ksize: int = 1, stride: int = 1, gn=None, act: int = 0,
+                 q: QParam = NOQ, pad_quantized: bool = False, ldo: Optional[int] = None,
+                 want_codes: bool = False):
+    """src NHWC ([batch, hs, ws, c], fp16 or fp32) -> fp16 A operand [M, ldo] (+ codes).
+    gn = (mean, rstd, gamma, beta) or None."""
+    c0 = src0.shape[-1]
+    c1 = src1.shape[-1] if src1 is not None else 0
+    pad = 1 if ksize == 3 else 0
+    ho = (h + 2 * pad - ksize) // stride + 1
+    wo = (w + 2 * pad - ksize) // stride + 1
+    K = ksize * ksize * (c0 + c1)
+    ldo = ldo or K
+    M = batch * ho * wo
+    out = torch.empty(M, ldo, dtype=torch.float16, device=src0.device)
+    codes = torch.empty(M, K, dtype=torch.uint8, device=src0.device) if want_codes else None
+    a = L.ProducerT(_p(src0), _p(src1), c0, c1, int(src0.dtype == torch.float32), batch, h, w, int(upsample),
+                    ksize, stride, pad,
+                    _p(gn[0]) if gn else None, _p(gn[1]) if gn else None, _p(gn[2]) if gn else None,
+                    _p(gn[3]) if gn else None, act, q.struct(), int(pad_quantized), _p(out), ldo, _p(codes))
+    L.check(L.lib().dgq_act_producer(C.byref(a), _stream()), "dgq_act_producer")
+    _count()
+    return (out, codes) if want_codes else out
+
+
+def gn_stats(src0: torch.Tensor, src1: Optional[torch.Tensor], batch: int, hw: int, eps: float):
+    c0 = src0.shape[-1]
+    c1 = src1.shape[-1] if src1 is not None else 0
+    dev = src0.device
+    mean = torch.empty(batch, 32, dtype=torch.float32, device=dev)
+    rstd = torch.empty(batch, 32, dtype=torch.float32, device=dev)
+    scratch = torch.empty(batch * 64 * 64, dtype=torch.float32, device=dev)
+    L.check(L.lib().dgq_gn_stats(_p(src0), _p(src1), c0, c1, batch, hw, eps, _p(mean), _p(rstd), _p(scratch),
+                                 _stream()), "dgq_gn_stats")
+    _count(2)
+    return mean, rstd
+
+
+def _row_outputs(x, qs):
+    m, c = x.shape
+    outs = [torch.empty(m, c, dtype=torch.float16, device=x.device) for _ in qs]
+    qarr = (L.QuantT * len(qs))(*[q.struct() for q in qs])
+    oarr = (C.c_void_p * len(qs))(*[o.data_ptr() for o in outs])
+    return outs, qarr, oarr
+
+
+def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, qs: Sequence[QParam]):
+    """x fp16 [m, c] -> [fp16 [m, c]] * len(qs)."""
+    outs, qarr, oarr = _row_outputs(x, qs)
+    L.check(L.lib().dgq_ln_quant(_p(x), x.shape[0], x.shape[1], _p(gamma), _p(beta), eps, len(qs), qarr, oarr,
+                                 _stream()), "dgq_ln_quant")
+    _count()
+    return outs
+
+
+def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False):
+    outs, qarr, oarr = _row_outputs(x, qs)
+    codes = [torch.empty(x.shape, dtype=torch.uint8, device=x.device) for _ in qs] if want_codes else None
+    carr = (C.c_void_p * len(qs))(*[c.data_ptr() for c in codes]) if want_codes else None
+    L.check(L.lib().dgq_row_quant(_p(x), int(x.dtype == torch.float32), x.shape[0], x.shape[1], len(qs), qarr,
+                                  oarr, carr, _stream()), "dgq_row_quant")
+    _count()
+    return (outs, codes) if want_codes else outs
+
+
+def geglu_quant(x: torch.Tensor, q: QParam) -> torch.Tensor:
+    m, f2 = x.shape
+    out = torch.empty(m, f2 // 2, dtype=torch.float16, device=x.device)
+    L.check(L.lib().dgq_geglu_quant(_p(x), m, f2 // 2, q.struct(), _p(out), _stream()), "dgq_geglu_quant")
+    _count()
+    return out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, temb=None, rows_per_batch: int = 0,
+         resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None):
+    """a fp16 [m, lda], b fp16 [n_pad, ldb] -> fp16 [m, n] (n multiple of 8)."""
+    m = a.shape[0]
+    k = k or min(a.shape[1], b.shape[1])
+    if out is None and not want_f32:
+        out = torch.empty(m, n, dtype=torch.float16, device=a.device)
+    out32 = torch.empty(m, n, dtype=torch.float32, device=a.device) if want_f32 else None
+    g = L.GemmT(_p(a), a.stride(0), _p(b), b.stride(0), m, n, k, _p(scale), _p(bias), _p(temb), rows_per_batch,
+                temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
+                _p(out), n, _p(out32))
+    L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
+    _count()
+    return out32 if want_f32 else out
+
+
+def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, transpose: bool = False,
+             skip_first: bool = False, q: QParam = NOQ) -> torch.Tensor:
+    tp = (t + 7) // 8 * 8
+    shape = (b, heads, dp, tp) if transpose else (b, heads, t, dp)
+    out = torch.empty(shape, dtype=torch.float16, device=x.device)
+    L.check(L.lib().dgq_qkv_pack(_p(x), x.stride(0), b, t, heads, d, dp, tp, int(transpose), int(skip_first),
+                                 q.struct(), _p(out), _stream()), "dgq_qkv_pack")
+    _count()
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map_mode: int, real_time: bool = False,
+              start_peak: bool = False, delta: Optional[torch.Tensor] = None, qmax: float = 255.0,
+              out: Optional[torch.Tensor] = None):
+    """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta)."""
+    b, heads, t, dp = q.shape
+    s, sp = k.shape[2], vt.shape[3]
+    dev = q.device
+    if out is None:
+        out = torch.empty(b * t, heads * d, dtype=torch.float16, device=dev)
+    row_max = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
+    gmax = torch.zeros(1 + 1024, dtype=torch.float32, device=dev)
+    a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
+                int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0))
+    L.check(L.lib().dgq_attention(C.byref(a), _stream()), "dgq_attention")
+    _count(3)
+    return out, gmax[:1]
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, *, f32: bool = False) -> torch.Tensor:
+    n = t.numel()
+    t = t.to(torch.float32).contiguous()
+    out = torch.empty(n, dim, dtype=torch.float32 if f32 else torch.float16, device=t.device)
+    L.check(L.lib().dgq_timestep_embedding(_p(t), n, dim, None if f32 else _p(out), _p(out) if f32 else None, dim,
+                                           _stream()), "dgq_timestep_embedding")
+    _count()
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: int) -> torch.Tensor:
+    b, c, h, w = x.shape
+    out = torch.empty(b, h, w, c_pad, dtype=torch.float16, device=x.device)
+    L.check(L.lib().dgq_nchw_to_nhwc(_p(x.contiguous()), b, c, h * w, c_pad, _p(out), _stream()), "dgq_nchw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, b: int, c: int, h: int, w: int) -> torch.Tensor:
+    out = torch.empty(b, c, h, w, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dgq_nhwc_to_nchw(_p(x), b, c, h * w, x.stride(-2), _p(out), _stream()), "dgq_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    L.check(L.lib().dgq_silu_f16(_p(x), x.numel(), _p(out), _stream()), "dgq_silu_f16")
+    _count()
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(a)
+    L.check(L.lib().dgq_add_f16(_p(a), _p(b), a.numel(), _p(out), _stream()), "dgq_add_f16")
+    _count()
+    return out

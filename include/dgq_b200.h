@@ -1,0 +1,184 @@
+/* dgq_b200 -- C ABI of the B200 (sm_100a) kernels behind DGQ's quantized UNet forward path.
+ *
+ * The reference (ugonfor/DGQ) has no FFI: its "plugin" boundary is the Python module API
+ * (quant.quant_model.QuantModel / quant.quant_layer.QuantLayer / quant.quant_block.*) and every
+ * kernel below replaces a sequence of eager ATen ops inside those modules.  Each entry point cites
+ * the reference code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing allocates,
+ *     nothing synchronises;
+ *   - return value: 0 on success, a positive cudaError_t, or DGQ_ERR_INVALID_VALUE (-1) when an
+ *     argument violates a documented constraint.  Nothing throws across the boundary;
+ *   - activations are fp16 ("half"), token-major / NHWC: a tensor (B, H, W, C) or (B, T, C) is a
+ *     row-major matrix [M = B*H*W, C]; scales are fp32.
+ */
+#ifndef DGQ_B200_H_
+#define DGQ_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGQ_ERR_INVALID_VALUE (-1)
+
+/* how a (delta, zero_point) pair is indexed -- the three shapes of the reference checkpoint
+ * (SURVEY.md 8a'): () scalar, (1,1,X) along the reduction axis, (1,X,1) along rows.          */
+#define DGQ_Q_NONE 0    /* no activation quantization (use_aq off / disable_aq)                */
+#define DGQ_Q_SCALAR 1  /* delta[0], zp[0]                                                      */
+#define DGQ_Q_KWISE 2   /* delta[k], k = position along K (linear: channel; conv: tap*C + c)    */
+#define DGQ_Q_ROWWISE 3 /* delta[m % period], m = output row (token / output pixel)             */
+
+typedef struct {
+  const float* delta; /* device, 1 or many entries depending on mode */
+  const float* zp;
+  int mode;   /* DGQ_Q_*            */
+  int period; /* DGQ_Q_ROWWISE only */
+  float qmax; /* 2^bits - 1         */
+} dgq_quant_t;
+
+int dgq_version(void);
+
+/* ---- UniformAffineQuantizer.forward, stand-alone (quant/quant_layer.py:295-299) -------------
+ * x viewed as [outer, period, inner]; delta/zp index = (i / inner) % period (period = 1: scalar).
+ * out_dq (fp32 de-quantised) and out_codes (u8 integer codes) are each optional.               */
+int dgq_fake_quant_f32(const float* x, int64_t n, const float* delta, const float* zp, int period,
+                       int64_t inner, float qmax, float* out_dq, uint8_t* out_codes, void* stream);
+
+/* ---- T2ILogQuantizer.forward (quant/quant_layer_text.py:96-105) -----------------------------
+ * code = clamp(rint(-log2(x / delta)), 0, qmax); out = 2^-code * delta.  `delta` is a device
+ * scalar; for real_time=True fill it first with dgq_max_f32.                                   */
+int dgq_t2i_log_quant_f32(const float* x, int64_t n, const float* delta, float qmax, float* out_dq,
+                          uint8_t* out_codes, void* stream);
+/* global max of x into *out (x.max(), quant_layer_text.py:97); scratch: >= 1024 floats         */
+int dgq_max_f32(const float* x, int64_t n, float* out, float* scratch, void* stream);
+
+/* ---- offline weight pack (replaces the per-forward wqtizer(self.w), quant/quant_layer.py:642-643;
+ *      AdaRound hard rounding quant/adaptive_rounding.py:51-70 when alpha != NULL) --------------
+ * w: fp32 [n, k_in] (conv: [Co, Ci, kh, kw] flattened, taps = kh*kw, ci = Ci).  Emits
+ *   codes   : u8 [n, k_out] integer codes in GEMM K order (tap-major: tap*ci_pad + c), optional;
+ *   packed4 : u8 [n, k_out/2] two 4-bit codes per byte (low nibble first), optional (bits == 4);
+ *   operand : fp16 [n_pad, k_out] holding (code - zp) exactly -- the tcgen05 B operand;
+ *   k_out = taps * ci_pad; rows n..n_pad-1 and channels ci..ci_pad-1 are zero.
+ * use_wq == 0: operand = fp16(w) (conv_in / conv_out stay FP, quant/quant_model.py:118-124).   */
+int dgq_pack_weight(const float* w, const float* delta, const float* zp, const float* alpha, int n,
+                    int ci, int taps, int ci_pad, int n_pad, float qmax, int use_wq, uint8_t* codes,
+                    uint8_t* packed4, void* operand, void* stream);
+
+/* ---- activation producer: fused [concat] -> [nearest x2] -> [GroupNorm] -> [SiLU] -> im2col ->
+ *      UniformAffineQuantizer, emitting the fp16 A operand of the following GEMM ----------------
+ * Replaces F.unfold + aqtizer (quant/quant_layer.py:630-641), GroupNorm+SiLU
+ * (quant/quant_block.py:100-110), torch.cat (diffusers_rewrite/sd.py:425,459) and nn.Upsample
+ * (sd.py:322-329).                                                                               */
+typedef struct {
+  const void* src0; /* [batch, hs, ws, c0]; fp16, or fp32 when src_is_f32                  */
+  const void* src1; /* optional second source, channels c0..c0+c1-1 (skip concat)           */
+  int c0, c1;       /* multiples of 8                                                       */
+  int src_is_f32;
+  int batch, h, w;  /* conv input size (after the optional upsample)                        */
+  int upsample;     /* 1: sources are (h/2, w/2)                                            */
+  int ksize, stride, pad; /* 1 or 3; 1 or 2; 0 or 1                                         */
+  const float* gn_mean;   /* [batch, 32] or NULL                                            */
+  const float* gn_rstd;
+  const float* gn_gamma;  /* [c0 + c1]                                                      */
+  const float* gn_beta;
+  int act;                /* 0 none, 1 SiLU                                                 */
+  dgq_quant_t q;
+  int pad_quantized;      /* 1: out-of-image taps = quantize(0) (unfold path) */
+  void* out;              /* fp16 [M, ldo], M = batch*ho*wo; columns >= K are zero          */
+  int ldo;
+  uint8_t* codes;         /* optional u8 [M, K] integer codes (verification)                */
+} dgq_producer_t;
+int dgq_act_producer(const dgq_producer_t* host_args, void* stream);
+
+/* GroupNorm(32, C) statistics over a (two-source) NHWC fp16 tensor -> mean, rstd [batch, 32].
+ * scratch: >= batch * 64 * 64 floats.                                                         */
+int dgq_gn_stats(const void* src0, const void* src1, int c0, int c1, int batch, int hw, float eps,
+                 float* mean, float* rstd, float* scratch, void* stream);
+
+/* LayerNorm(C, eps) + up to three UniformAffineQuantizers of the same normalised row
+ * (norm1 -> to_q/to_k/to_v, diffusers_rewrite/sd.py:252-269; quant/quant_layer.py:640-641).
+ * x: fp16 [m, c]; out[i]: fp16 [m, c].                                                         */
+int dgq_ln_quant(const void* x, int m, int c, const float* gamma, const float* beta, float eps,
+                 int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream);
+
+/* row quantizer without a norm (cross-attention to_k/to_v on encoder_hidden_states, fp32 or fp16
+ * input [m, c]) -- same outputs as dgq_ln_quant                                                */
+int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_out, const dgq_quant_t* host_q,
+                  void* const* host_out, uint8_t* const* host_codes, void* stream);
+
+/* GEGLU (diffusers_rewrite/sd.py:215-218: x1 * gelu_erf(x2)) + quantizer of ff.net.2.
+ * x: fp16 [m, 2f] -> out fp16 [m, f]                                                            */
+int dgq_geglu_quant(const void* x, int m, int f, dgq_quant_t q, void* out, void* stream);
+
+/* ---- qGEMM: C[m, n] = (A[m, k] . B[n, k]^T) * scale[n] + bias[n] (+ temb[m / rows_per_batch, n])
+ *      (+ resid[m, n]) on tcgen05/TMEM, TMA-fed (replaces F.linear / F.conv2d / W.view(Co,-1) @ x_unf,
+ *      quant/quant_layer.py:649-659; residual and temb adds quant/quant_block.py:105-117,165-186).
+ * A: fp16 [m, lda]; B: fp16 [n_pad, ldb] = (code - zp) from dgq_pack_weight; k multiple of 8;
+ * out: fp16 [m, ldc] (and/or out_f32 [m, ldc]); ldc, n multiples of 8.                          */
+typedef struct {
+  const void* a; int lda;
+  const void* b; int ldb;
+  int m, n, k;
+  const float* scale;  /* [n] per-out-channel weight delta, or NULL (=1) */
+  const float* bias;   /* [n] or NULL */
+  const void* temb;    /* fp16 [m / rows_per_batch, ld_temb] or NULL */
+  int rows_per_batch, ld_temb;
+  const void* resid;   /* fp16 [m, ld_resid] or NULL */
+  int ld_resid;
+  void* out; int ldc;  /* fp16 */
+  float* out_f32;      /* optional fp32 copy of the result */
+} dgq_gemm_t;
+int dgq_gemm_f16(const dgq_gemm_t* host_args, void* stream);
+
+/* ---- attention with quantised operands and quantised softmax map
+ *      (Attention.Attention_forward, diffusers_rewrite/sd.py:151-207; T2ILogQuantizer) ---------
+ * dgq_qkv_pack: GEMM output [b*t, heads*d] fp16 -> quantised, head-split, zero-padded operand:
+ *   transpose == 0: out fp16 [b, heads, t, dp]         (Q and K)
+ *   transpose == 1: out fp16 [b, heads, dp, tp]        (V^T), tp = round_up(t, 8)
+ *   q.mode: NONE / SCALAR / KWISE (index d) / ROWWISE (index t - skip_first).
+ *   skip_first == 1: token 0 bypasses the quantizer (start-peak, sd.py:176-180).               */
+int dgq_qkv_pack(const void* x, int ldx, int b, int t, int heads, int d, int dp, int tp,
+                 int transpose, int skip_first, dgq_quant_t q, void* out, void* stream);
+
+#define DGQ_MAP_NONE 0    /* use_aq off: plain softmax                                   */
+#define DGQ_MAP_UNIFORM 1 /* UniformAffineQuantizer, always_zero (zp = 0)                */
+#define DGQ_MAP_LOG2 2    /* T2ILogQuantizer                                             */
+typedef struct {
+  const void* q;   /* fp16 [b, heads, t, dp]  */
+  const void* k;   /* fp16 [b, heads, s, dp]  */
+  const void* vt;  /* fp16 [b, heads, dp, sp] */
+  int b, heads, t, s, sp, d, dp;
+  float scale;          /* d^-0.5 */
+  int map_mode;         /* DGQ_MAP_* */
+  int real_time;        /* LOG2: delta = max over the whole (b,h,t,s) map of this call */
+  int start_peak;       /* column 0 bypasses the map quantizer (sd.py:191-195) */
+  const float* delta;   /* device scalar (static delta); ignored when real_time */
+  float qmax;
+  float* row_max;       /* scratch [b*heads*t] */
+  float* row_sum;       /* scratch [b*heads*t] */
+  float* gmax;          /* scratch [1 + 1024]; gmax[0] receives the real-time delta */
+  void* out;            /* fp16 [b*t, ldo], head h at columns h*d .. h*d+d-1 */
+  int ldo;
+} dgq_attn_t;
+int dgq_attention(const dgq_attn_t* host_args, void* stream);
+
+/* ---- small glue kernels ---------------------------------------------------------------------*/
+/* Timesteps.forward (diffusers_rewrite/sd.py:25-39): [n] fp32 -> fp16/fp32 [n, dim] (cos | sin) */
+int dgq_timestep_embedding(const float* t, int n, int dim, void* out_f16, float* out_f32, int ldo,
+                           void* stream);
+/* fp32 NCHW -> fp16 NHWC with channel padding (conv_in input), and back (conv_out result)       */
+int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, void* stream);
+int dgq_nhwc_to_nchw(const void* x, int b, int c, int hw, int ldx, float* out, void* stream);
+/* y = act(x) elementwise on fp16 (SiLU on the time embedding, quant/quant_block.py:107)        */
+int dgq_silu_f16(const void* x, int64_t n, void* out, void* stream);
+/* out = a + b (fp16)                                                                            */
+int dgq_add_f16(const void* a, const void* b, int64_t n, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGQ_B200_H_ */

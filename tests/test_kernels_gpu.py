@@ -1,0 +1,295 @@
+"""Parity of the individual CUDA kernels (through the C ABI) against the CPU oracle.
+Integer codes must be bit-exact; fp16 GEMM outputs within max-rel-err 1e-2 (north_star)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dgq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+REL_TOL = 1e-2  # north_star: per-layer max rel err <= 1e-2 with 16-bit operands
+
+
+def rel_err(a, b):
+    return ((a.float().cpu() - b.float().cpu()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def group_params(g, n, level, view):
+    lab = torch.randint(0, 8, (n,), generator=g)
+    lo = -(torch.rand(8, generator=g) * 3 + 1)
+    hi = torch.rand(8, generator=g) * 3 + 1
+    lo[0], hi[0] = 0.5, 2.0     # zp < 0
+    lo[1], hi[1] = -3.0, -0.4   # zp > level-1
+    d = (hi - lo) / (level - 1)
+    z = torch.round(-lo / d)
+    return d[lab].view(view), z[lab].view(view)
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [8, 6])
+@pytest.mark.parametrize("layout", ["scalar", "in", "out"])
+def test_fake_quant_bit_exact(ops_golden, bits, layout):
+    from dgq_b200 import ops
+    c = ops_golden[f"uaq_a{bits}_{layout}"]
+    x = torch.randn(2, 48, 40, generator=torch.Generator().manual_seed(c["seed"])) * 2
+    d, z = c["delta"].float(), c["zp"].float()
+    period, inner = {"scalar": (1, 1), "in": (40, 1), "out": (48, 40)}[layout]
+    dd = d.reshape(-1).to(DEV).contiguous()
+    zz = z.reshape(-1).expand(dd.numel()).to(DEV).contiguous()
+    out, codes = ops.fake_quant(x.to(DEV), dd, zz, period, inner, float(2 ** bits - 1), want_codes=True)
+    assert torch.equal(out.cpu(), c["out"])                      # the reference's own output
+    assert torch.equal(codes.cpu().float(), O.uaq_codes(x, d, z, 2 ** bits))
+
+
+def test_fake_quant_large_and_ragged():
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 3, 5, 1027, 1 << 20):
+        x = torch.randn(n, generator=g) * 4
+        d, z = torch.tensor([0.0371]), torch.tensor([131.0])
+        out, codes = ops.fake_quant(x.to(DEV), d.to(DEV), z.to(DEV), 1, 1, 255.0, want_codes=True)
+        assert torch.equal(out.cpu(), O.uaq_fake_quant(x, d, z, 256))
+        assert torch.equal(codes.cpu().float(), O.uaq_codes(x, d, z, 256))
+
+
+@pytest.mark.parametrize("rt", [0, 1])
+def test_t2i_log_quant(ops_golden, rt):
+    from dgq_b200 import ops
+    c = ops_golden[f"t2i_log_rt{rt}"]
+    p = torch.softmax(torch.randn(2, 4, 33, 77, generator=torch.Generator().manual_seed(c["seed"])) * 3, dim=-1)
+    delta = None if rt else c["delta"].reshape(1).to(DEV)
+    out, codes = ops.t2i_log_quant(p.to(DEV).contiguous(), delta, 255.0, want_codes=True)
+    ref_d = p.max() if rt else c["delta"]
+    ref_codes = O.t2i_log_codes(p, ref_d, 256)
+    # log2f may differ from the host libm by 1 ulp: tolerate codes only where -log2(x/delta) is a
+    # rounding tie to within 1e-5 (documented residual)
+    t = -torch.log2(p / ref_d)
+    tie = (t - torch.floor(t) - 0.5).abs() < 1e-5
+    bad = (codes.cpu().float() != ref_codes) & ~tie
+    assert bad.sum().item() == 0
+    mism = (out.cpu() != c["out"]) & ~tie
+    assert mism.sum().item() == 0
+    assert (codes.cpu().float() != ref_codes).float().mean().item() < 1e-4
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_pack_weight(ops_golden, bits):
+    from dgq_b200 import ops
+    c = ops_golden[f"wq_w{bits}"]
+    w = torch.randn(24, 16, 3, 3, generator=torch.Generator().manual_seed(c["seed"])) * 0.05
+    level = 2 ** bits
+    d, z = c["delta"], c["zp"]
+    for alpha in (None, c["alpha"]):
+        operand, codes, packed = ops.pack_weight(w.to(DEV), d, z, alpha, float(level - 1), True,
+                                                 want_codes=True, want_packed4=(bits == 4))
+        ref = O.uaq_codes(w, d, z, level) if alpha is None else O.adaround_codes(w, d, z, alpha, level)
+        ref_k = ref.permute(0, 2, 3, 1).reshape(24, -1)            # tap-major K order
+        assert torch.equal(codes.cpu().float(), ref_k)
+        zk = z.reshape(24, 1)
+        assert torch.equal(operand.cpu().float(), ref_k - zk)
+        # de-quantised weight == the reference's own output
+        gold = c["out"] if alpha is None else c["ada_out"]
+        wdq = (d.reshape(24, 1) * operand.cpu().float()).reshape(24, 3, 3, 16).permute(0, 3, 1, 2)
+        assert torch.equal(wdq, gold)
+        if bits == 4:
+            lo, hi = packed.cpu() & 0xF, packed.cpu() >> 4
+            assert torch.equal(torch.stack([lo, hi], -1).reshape(24, -1).float(), ref_k)
+
+
+# ------------------------------------------------------------------------------------------
+def _unfold_ref(x, k, s, delta, zp, grouped, level=256):
+    """reference order: unfold (B, C*k*k, L) then quantise (quant_layer.py:630-641)."""
+    if grouped:
+        xu = F.unfold(x, kernel_size=k, padding=k // 2, stride=s)
+        codes = O.uaq_codes(xu, delta, zp, level)
+        dq = delta * (codes - zp)
+    else:  # conv2d path: quantise the image, zero padding stays exactly zero
+        codes = F.unfold(O.uaq_codes(x, delta, zp, level) + 1, kernel_size=k, padding=k // 2, stride=s) - 1
+        dq = F.unfold(O.uaq_fake_quant(x, delta, zp, level), kernel_size=k, padding=k // 2, stride=s)
+    return codes, dq  # (B, C*k*k, L)
+
+
+@pytest.mark.parametrize("k,s,ci,hw", [(3, 1, 32, 12), (3, 2, 32, 12), (1, 1, 64, 8), (3, 1, 320, 16)])
+@pytest.mark.parametrize("mode", ["g1", "g1u", "kwise", "rowwise"])
+def test_act_producer_codes_bit_exact(k, s, ci, hw, mode):
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(1000 + k * 10 + s)
+    bsz = 2
+    x = torch.randn(bsz, ci, hw, hw, generator=g) * 1.5
+    ho = (hw + 2 * (k // 2) - k) // s + 1
+    L, K = ho * ho, ci * k * k
+    if mode in ("g1", "g1u"):
+        d, z = torch.tensor(0.031), torch.tensor(121.0)
+    elif mode == "kwise":
+        d, z = group_params(g, K, 256, (1, -1, 1))
+    else:
+        d, z = group_params(g, L, 256, (1, 1, -1))
+    grouped = mode != "g1"
+    codes_ref, dq_ref = _unfold_ref(x, k, s, d, z, grouped)
+    # reference K order c*k*k + tap -> ours tap*C + c
+    kperm = (torch.arange(ci).view(1, ci) * (k * k) + torch.arange(k * k).view(k * k, 1)).reshape(-1)
+    if mode == "kwise":
+        q = ops.qparam_from_ckpt(d.view(1, 1, -1), z.view(1, 1, -1), 255.0, DEV, kperm=kperm)
+    elif mode == "rowwise":
+        q = ops.qparam_from_ckpt(d.view(1, -1, 1), z.view(1, -1, 1), 255.0, DEV)
+    else:
+        q = ops.qparam_from_ckpt(d, z, 255.0, DEV)
+    xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out, codes = ops.act_producer(xin, batch=bsz, h=hw, w=hw, ksize=k, stride=s, q=q, pad_quantized=grouped,
+                                  want_codes=True)
+    codes_ref = codes_ref[:, kperm, :].permute(0, 2, 1).reshape(bsz * L, K)
+    dq_ref = dq_ref[:, kperm, :].permute(0, 2, 1).reshape(bsz * L, K)
+    if not grouped:  # exact-zero padding carries code -1 in the reference helper: producer writes 0
+        codes_ref = codes_ref.clamp_min(0)
+    assert torch.equal(codes.cpu().float(), codes_ref)
+    assert torch.equal(out.cpu().float(), dq_ref.half().float())
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 320, 128), (100, 8, 72), (154, 640, 768),
+                                   (16, 1280, 320), (4096, 320, 2880), (1024, 1280, 1280), (300, 2560, 640)])
+def test_gemm_against_fp32(m, n, k):
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = (torch.randn(m, k, generator=g) * 0.7).half()
+    b = torch.randint(-15, 16, (n, k), generator=g).half()
+    scale = torch.rand(n, generator=g) * 0.01 + 0.001
+    bias = torch.randn(n, generator=g) * 0.1
+    ref = (a.float() @ b.float().t()) * scale + bias
+    out = ops.gemm(a.to(DEV), b.to(DEV), n, scale=scale.to(DEV), bias=bias.to(DEV))
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    out32 = ops.gemm(a.to(DEV), b.to(DEV), n, scale=scale.to(DEV), bias=bias.to(DEV), want_f32=True)
+    assert rel_err(out32, ref) < 1e-5, rel_err(out32, ref)
+
+
+def test_gemm_epilogue_temb_resid():
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    bsz, rows, n, k = 3, 64, 320, 256
+    m = bsz * rows
+    a = (torch.randn(m, k, generator=g)).half()
+    b = torch.randint(-7, 8, (n, k), generator=g).half()
+    temb = torch.randn(bsz, n, generator=g).half()
+    resid = torch.randn(m, n, generator=g).half()
+    ref = a.float() @ b.float().t() + temb.float().repeat_interleave(rows, 0) + resid.float()
+    out = ops.gemm(a.to(DEV), b.to(DEV), n, temb=temb.to(DEV), rows_per_batch=rows, resid=resid.to(DEV),
+                   want_f32=True)
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_gemm_repeatable_many_tiles():
+    """persistent loop + TMEM double buffering: > 148 tiles, run twice, identical bits."""
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    m, n, k = 8192, 1280, 640
+    a = torch.randn(m, k, generator=g).half().to(DEV)
+    b = torch.randint(-15, 16, (n, k), generator=g).half().to(DEV)
+    o1 = ops.gemm(a, b, n, want_f32=True)
+    o2 = ops.gemm(a, b, n, want_f32=True)
+    assert torch.equal(o1, o2)
+    ref = a.float() @ b.float().t()
+    assert rel_err(o1, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["g1", "kwise", "rowwise"])
+def test_config1_quant_layer(ops_golden, mode):
+    """BASELINE config 1 through producer + pack + qGEMM vs the reference's own output."""
+    from dgq_b200 import ops
+    c = ops_golden[f"config1_{mode}"]
+    g = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    layer = torch.nn.Conv2d(320, 320, 3, 1, 1)
+    x = torch.randn(1, 320, 64, 64, generator=g)
+    kperm = (torch.arange(320).view(1, 320) * 9 + torch.arange(9).view(9, 1)).reshape(-1)
+    q = ops.qparam_from_ckpt(c["delta"], c["zp"], 255.0, DEV, kperm=kperm)
+    operand, _, _ = ops.pack_weight(layer.weight.detach().to(DEV), c["wdelta"], c["wzp"], None, 15.0, True)
+    a = ops.act_producer(x.permute(0, 2, 3, 1).contiguous().to(DEV), batch=1, h=64, w=64, ksize=3, q=q,
+                         pad_quantized=c["grouped"])
+    y = ops.gemm(a, operand, 320, scale=c["wdelta"].reshape(-1).to(DEV), bias=layer.bias.detach().to(DEV),
+                 want_f32=True)
+    y = y.reshape(1, 64, 64, 320).permute(0, 3, 1, 2).reshape(-1)[::37]
+    assert rel_err(y, c["out_sub"]) < REL_TOL, rel_err(y, c["out_sub"])
+
+
+# ------------------------------------------------------------------------------------------
+def test_gn_silu_producer():
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    bsz, c0, c1, hw = 2, 320, 640, 16
+    x0 = torch.randn(bsz, hw, hw, c0, generator=g).half()
+    x1 = (torch.randn(bsz, hw, hw, c1, generator=g) * 2 + 0.5).half()
+    gamma, beta = torch.randn(c0 + c1, generator=g), torch.randn(c0 + c1, generator=g)
+    mean, rstd = ops.gn_stats(x0.to(DEV), x1.to(DEV), bsz, hw * hw, 1e-5)
+    xc = torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2)
+    xg = xc.reshape(bsz, 32, -1)
+    assert torch.allclose(mean.cpu(), xg.mean(-1), atol=1e-4)
+    assert torch.allclose(rstd.cpu(), 1 / torch.sqrt(xg.var(-1, unbiased=False) + 1e-5), rtol=1e-4)
+    ref = F.silu(F.group_norm(xc, 32, gamma, beta, 1e-5))
+    out = ops.act_producer(x0.to(DEV), src1=x1.to(DEV), batch=bsz, h=hw, w=hw, ksize=1,
+                           gn=(mean, rstd, gamma.to(DEV), beta.to(DEV)), act=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(bsz * hw * hw, -1)
+    assert (out.cpu().float() - ref).abs().max().item() < 5e-3
+    # upsample + 3x3: compare with unfold of the interpolated tensor
+    xs = x0[:, :8, :8].contiguous()
+    up = F.interpolate(xs.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.unfold(up, 3, padding=1).view(bsz, c0, 9, -1).permute(0, 3, 2, 1).reshape(bsz * 256, 9 * c0)
+    out = ops.act_producer(xs.to(DEV), batch=bsz, h=16, w=16, upsample=True, ksize=3)
+    assert torch.equal(out.cpu().float(), ref)
+
+
+def test_ln_quant_and_geglu():
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(78)
+    m, c = 300, 640
+    x = (torch.randn(m, c, generator=g) * 1.3 + 0.2).half()
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g)
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    dk, zk = group_params(g, c, 256, (1, 1, -1))
+    dr, zr = group_params(g, 100, 256, (1, -1, 1))
+    qs = [ops.NOQ, ops.qparam_from_ckpt(dk, zk, 255.0, DEV), ops.qparam_from_ckpt(dr, zr, 255.0, DEV)]
+    outs = ops.ln_quant(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, qs)
+    assert (outs[0].cpu().float() - ref).abs().max().item() < 4e-3
+    # quantised outputs: allow one code of slack where LN rounding moves a value across a boundary
+    r3 = ref.view(3, 100, c)
+    for o, d, z in ((outs[1], dk, zk), (outs[2], dr, zr)):
+        want = O.uaq_fake_quant(r3, d, z, 256).reshape(m, c)
+        step = d.expand(1, 100, c) if d.shape[1] == 100 else d.expand(1, 100, c)
+        diff = (o.cpu().float() - want).abs()
+        assert (diff <= step.expand(3, 100, c).reshape(m, c) * 1.01 + 2e-3).all()
+        assert (diff > 2e-3).float().mean().item() < 2e-3
+    # GEGLU
+    f = 320
+    h = (torch.randn(m, 2 * f, generator=g)).half()
+    out = ops.geglu_quant(h.to(DEV), ops.NOQ)
+    ref = h[:, :f].float() * F.gelu(h[:, f:].float())
+    assert (out.cpu().float() - ref).abs().max().item() < 3e-3
+
+
+def test_row_quant_fp32_bit_exact():
+    from dgq_b200 import ops
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn(2 * 77, 768, generator=g)
+    dk, zk = group_params(g, 768, 256, (1, 1, -1))
+    dr, zr = group_params(g, 77, 256, (1, -1, 1))
+    qs = [ops.qparam_from_ckpt(dk, zk, 255.0, DEV), ops.qparam_from_ckpt(dr, zr, 255.0, DEV)]
+    outs, codes = ops.row_quant(x.to(DEV), qs, want_codes=True)
+    x3 = x.view(2, 77, 768)
+    assert torch.equal(codes[0].cpu().float(), O.uaq_codes(x3, dk, zk, 256).reshape(-1, 768))
+    assert torch.equal(codes[1].cpu().float(), O.uaq_codes(x3, dr, zr, 256).reshape(-1, 768))
+    assert torch.equal(outs[0].cpu().float(), O.uaq_fake_quant(x3, dk, zk, 256).reshape(-1, 768).half().float())
+
+
+def test_glue_kernels():
+    from dgq_b200 import ops
+    t = torch.tensor([981.0, 1.0, 500.0])
+    e = ops.timestep_embedding(t.to(DEV), 320, f32=True)
+    assert torch.allclose(e.cpu(), O.timestep_embedding(t, 320), atol=2e-4)
+    x = torch.randn(2, 4, 8, 8)
+    y = ops.nchw_to_nhwc(x.to(DEV), 8)
+    assert torch.equal(y.cpu()[..., :4].float(), x.permute(0, 2, 3, 1).half().float())
+    assert (y.cpu()[..., 4:] == 0).all()
+    z = ops.nhwc_to_nchw(y, 2, 4, 8, 8)
+    assert torch.equal(z.cpu(), x.half().float())
