@@ -12,7 +12,7 @@ SYMBOLS = [
     "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight",
     "dgq_act_producer", "dgq_gn_stats", "dgq_ln_quant", "dgq_row_quant", "dgq_geglu_quant",
     "dgq_gemm_f16", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
-    "dgq_nhwc_to_nchw", "dgq_silu_f16", "dgq_add_f16",
+    "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add",
 ]
 
 Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE = 0, 1, 2, 3
@@ -38,7 +38,7 @@ class GemmT(C.Structure):
                 ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("scale", C.c_void_p),
                 ("bias", C.c_void_p), ("temb", C.c_void_p), ("rows_per_batch", C.c_int),
                 ("ld_temb", C.c_int), ("resid", C.c_void_p), ("ld_resid", C.c_int),
-                ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p)]
+                ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p), ("ep_is_f32", C.c_int)]
 
 
 class AttnT(C.Structure):
@@ -47,7 +47,7 @@ class AttnT(C.Structure):
                 ("dp", C.c_int), ("scale", C.c_float), ("map_mode", C.c_int), ("real_time", C.c_int),
                 ("start_peak", C.c_int), ("delta", C.c_void_p), ("qmax", C.c_float),
                 ("row_max", C.c_void_p), ("row_sum", C.c_void_p), ("gmax", C.c_void_p),
-                ("out", C.c_void_p), ("ldo", C.c_int)]
+                ("out", C.c_void_p), ("ldo", C.c_int), ("out_is_f32", C.c_int), ("codes", C.c_void_p)]
 
 
 _lib = None
@@ -69,18 +69,18 @@ def lib() -> C.CDLL:
             "dgq_max_f32": [vp, i64, vp, vp, vp],
             "dgq_pack_weight": [vp, vp, vp, vp, i, i, i, i, i, f, i, vp, vp, vp, vp],
             "dgq_act_producer": [C.POINTER(ProducerT), vp],
-            "dgq_gn_stats": [vp, vp, i, i, i, i, f, vp, vp, vp, vp],
-            "dgq_ln_quant": [vp, i, i, vp, vp, f, i, C.POINTER(QuantT), C.POINTER(vp), vp],
+            "dgq_gn_stats": [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp],
+            "dgq_ln_quant": [vp, i, i, i, vp, vp, f, i, C.POINTER(QuantT), C.POINTER(vp), vp],
             "dgq_row_quant": [vp, i, i, i, i, C.POINTER(QuantT), C.POINTER(vp), C.POINTER(vp), vp],
-            "dgq_geglu_quant": [vp, i, i, QuantT, vp, vp],
+            "dgq_geglu_quant": [vp, i, i, i, QuantT, vp, vp],
             "dgq_gemm_f16": [C.POINTER(GemmT), vp],
-            "dgq_qkv_pack": [vp, i, i, i, i, i, i, i, i, i, QuantT, vp, vp],
+            "dgq_qkv_pack": [vp, i, i, i, i, i, i, i, i, i, i, QuantT, vp, vp],
             "dgq_attention": [C.POINTER(AttnT), vp],
             "dgq_timestep_embedding": [vp, i, i, vp, vp, i, vp],
-            "dgq_nchw_to_nhwc": [vp, i, i, i, i, vp, vp],
-            "dgq_nhwc_to_nchw": [vp, i, i, i, i, vp, vp],
-            "dgq_silu_f16": [vp, i64, vp, vp],
-            "dgq_add_f16": [vp, vp, i64, vp, vp],
+            "dgq_nchw_to_nhwc": [vp, i, i, i, i, vp, i, vp],
+            "dgq_nhwc_to_nchw": [vp, i, i, i, i, i, vp, vp],
+            "dgq_silu": [vp, i, i64, vp, vp],
+            "dgq_add": [vp, vp, i, i64, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(l, name)

@@ -35,13 +35,14 @@ struct GemmDev {
   int m_tiles, n_tiles;
   const float* scale;
   const float* bias;
-  const __half* temb;
+  const void* temb;
   int rows_per_batch, ld_temb;
-  const __half* resid;
+  const void* resid;
   int ld_resid;
   __half* out;
   int ldc;
   float* out_f32;
+  int ep_is_f32;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -136,10 +137,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       tc_fence_after();
       const int row = m_blk * kBM + quad * 32 + lane;
       const bool row_ok = row < p.m;
-      const __half* temb_row = (p.temb != nullptr && row_ok)
-                                   ? p.temb + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb
-                                   : nullptr;
-      const __half* resid_row = (p.resid != nullptr && row_ok) ? p.resid + static_cast<size_t>(row) * p.ld_resid : nullptr;
+      const size_t esz = p.ep_is_f32 ? 4 : 2;
+      const char* temb_row = (p.temb != nullptr && row_ok)
+                                 ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
+                                 : nullptr;
+      const char* resid_row = (p.resid != nullptr && row_ok)
+                                  ? static_cast<const char*>(p.resid) + static_cast<size_t>(row) * p.ld_resid * esz
+                                  : nullptr;
       const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = 0; c < p.bn; c += 32) {
         uint32_t r[32];
@@ -168,13 +172,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               }
               if (temb_row != nullptr) {
                 float t[8];
-                load8(temb_row + n, t);
+                if (p.ep_is_f32) load8(reinterpret_cast<const float*>(temb_row) + n, t);
+                else load8(reinterpret_cast<const __half*>(temb_row) + n, t);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += t[i];
               }
               if (resid_row != nullptr) {
                 float t[8];
-                load8(resid_row + n, t);
+                if (p.ep_is_f32) load8(reinterpret_cast<const float*>(resid_row) + n, t);
+                else load8(reinterpret_cast<const __half*>(resid_row) + n, t);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] += t[i];
               }
@@ -270,10 +276,11 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   p.m_tiles = (a->m + kBM - 1) / kBM;
   p.n_tiles = (a->n + p.bn - 1) / p.bn;
   p.scale = a->scale; p.bias = a->bias;
-  p.temb = static_cast<const __half*>(a->temb);
+  p.temb = a->temb;
   p.rows_per_batch = a->rows_per_batch; p.ld_temb = a->ld_temb;
-  p.resid = static_cast<const __half*>(a->resid); p.ld_resid = a->ld_resid;
+  p.resid = a->resid; p.ld_resid = a->ld_resid;
   p.out = static_cast<__half*>(a->out); p.ldc = a->ldc; p.out_f32 = a->out_f32;
+  p.ep_is_f32 = a->ep_is_f32;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM);

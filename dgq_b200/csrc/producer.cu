@@ -25,6 +25,11 @@ struct QuantDev {
 
 static QuantDev to_dev(const dgq_quant_t& q) { return QuantDev{q.delta, q.zp, q.mode, q.period, q.qmax}; }
 
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_f(float v, float* o) { *o = v; }
+__device__ __forceinline__ void from_f(float v, __half* o) { *o = __float2half_rn(v); }
+
 // quantize 8 consecutive K positions k0..k0+7 of row `row`; returns de-quantised values in v
 __device__ __forceinline__ void quant8(const QuantDev& q, float (&v)[8], int k0, int row, uint8_t* codes8) {
   if (q.mode == DGQ_Q_NONE) return;
@@ -128,8 +133,9 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
 // GroupNorm statistics, stage 1: CTA (b, chunk) sums rows [chunk*rows_per, ...) per channel, folds
 // channels into the 32 groups, writes partial (sum, sumsq) to scratch[b][chunk][32][2].
 constexpr int kGnMaxC = 2560;
-__global__ void __launch_bounds__(256) gn_partial_kernel(const __half* __restrict__ src0,
-                                                         const __half* __restrict__ src1, int c0, int c1, int hw,
+template <typename TIn>
+__global__ void __launch_bounds__(256) gn_partial_kernel(const TIn* __restrict__ src0,
+                                                         const TIn* __restrict__ src1, int c0, int c1, int hw,
                                                          int rows_per, int chunks, float* __restrict__ scratch) {
   const int C = c0 + c1;
   const int cpg = C >> 5;
@@ -195,9 +201,9 @@ struct RowQuantDev {
   uint8_t* codes[3];
   int n_out;
 };
-constexpr int kMaxVecPerLane = 8;  // supports C <= 8*8*32 = 2048
 
-template <typename TIn, bool kNorm>
+// kMaxVecPerLane * 256 = widest supported row (5: C <= 1280, the LayerNorm widths; 12: C <= 3072)
+template <typename TIn, bool kNorm, int kMaxVecPerLane>
 __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ x, int m, int c,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
@@ -262,7 +268,8 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) geglu_quant_kernel(const __half* __restrict__ x, int m, int f,
+template <typename TIn>
+__global__ void __launch_bounds__(256) geglu_quant_kernel(const TIn* __restrict__ x, int m, int f,
                                                           const QuantDev q, __half* __restrict__ out) {
   const int fvec = f >> 3;
   const int64_t total = static_cast<int64_t>(m) * fvec;
@@ -283,7 +290,8 @@ __global__ void __launch_bounds__(256) geglu_quant_kernel(const __half* __restri
 // ------------------------------------------------------------------------------------------
 // x [b*t, ldx] (head h = columns h*d..) -> out [b, heads, t, dp] (transpose == 0)
 //                                        or out [b, heads, dp, tp] (transpose == 1)
-__global__ void __launch_bounds__(256) qkv_pack_kernel(const __half* __restrict__ x, int ldx, int b, int t,
+template <typename TIn>
+__global__ void __launch_bounds__(256) qkv_pack_kernel(const TIn* __restrict__ x, int ldx, int b, int t,
                                                        int heads, int d, int dp, int tp, int transpose,
                                                        int skip_first, const QuantDev q, __half* __restrict__ out) {
   if (!transpose) {
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(256) qkv_pack_kernel(const __half* __restrict_
         const int tt = t0 + i;
         float val = 0.f;
         if (dd < d && tt < t) {
-          val = __half2float(x[(static_cast<size_t>(bb) * t + tt) * ldx + hh * d + dd]);
+          val = to_f(x[(static_cast<size_t>(bb) * t + tt) * ldx + hh * d + dd]);
           if (q.mode != DGQ_Q_NONE && !(skip_first && tt == 0)) {
             const int j = q.mode == DGQ_Q_KWISE ? dd : (q.mode == DGQ_Q_ROWWISE ? tt - skip_first : 0);
             const float dl = __ldg(q.delta + j), z = __ldg(q.zp + j);
@@ -363,8 +371,9 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
   }
 }
 
+template <typename TOut>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int b, int c, int hw, int c_pad,
-                                    __half* __restrict__ out) {
+                                    TOut* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(b) * hw * c_pad;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -372,10 +381,11 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int b, int c, i
     const int64_t r = i / c_pad;
     const int p = static_cast<int>(r % hw);
     const int bb = static_cast<int>(r / hw);
-    out[i] = cc < c ? __float2half_rn(x[(static_cast<size_t>(bb) * c + cc) * hw + p]) : __float2half_rn(0.f);
+    from_f(cc < c ? x[(static_cast<size_t>(bb) * c + cc) * hw + p] : 0.f, out + i);
   }
 }
-__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int b, int c, int hw, int ldx,
+template <typename TIn>
+__global__ void nhwc_to_nchw_kernel(const TIn* __restrict__ x, int b, int c, int hw, int ldx,
                                     float* __restrict__ out) {
   const int64_t total = static_cast<int64_t>(b) * c * hw;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -384,19 +394,22 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, int b, int c, 
     const int64_t r = i / hw;
     const int cc = static_cast<int>(r % c);
     const int bb = static_cast<int>(r / c);
-    out[i] = __half2float(x[(static_cast<size_t>(bb) * hw + p) * ldx + cc]);
+    out[i] = to_f(x[(static_cast<size_t>(bb) * hw + p) * ldx + cc]);
   }
 }
-__global__ void silu_kernel(const __half* __restrict__ x, int64_t n, __half* __restrict__ out) {
+template <typename T>
+__global__ void silu_kernel(const T* __restrict__ x, int64_t n, T* __restrict__ out) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    out[i] = __float2half_rn(silu_f(__half2float(x[i])));
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = to_f(x[i]);
+    from_f(v / (1.0f + expf(-v)), out + i);
+  }
 }
-__global__ void add_kernel(const __half* __restrict__ a, const __half* __restrict__ b, int64_t n,
-                           __half* __restrict__ out) {
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n, T* __restrict__ out) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    out[i] = __float2half_rn(__half2float(a[i]) + __half2float(b[i]));
+    from_f(to_f(a[i]) + to_f(b[i]), out + i);
 }
 
 static int grid_for(int64_t work, int block, int max_blocks) {
@@ -447,8 +460,8 @@ extern "C" int dgq_act_producer(const dgq_producer_t* a, void* stream) {
   DGQ_RETURN_LAST_ERROR();
 }
 
-extern "C" int dgq_gn_stats(const void* src0, const void* src1, int c0, int c1, int batch, int hw, float eps,
-                            float* mean, float* rstd, float* scratch, void* stream) {
+extern "C" int dgq_gn_stats(const void* src0, const void* src1, int src_is_f32, int c0, int c1, int batch, int hw,
+                            float eps, float* mean, float* rstd, float* scratch, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(src0 != nullptr && mean != nullptr && rstd != nullptr && scratch != nullptr);
   DGQ_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 && (c0 + c1) % 32 == 0);
@@ -458,9 +471,14 @@ extern "C" int dgq_gn_stats(const void* src0, const void* src1, int c0, int c1, 
   if (chunks > 64) chunks = 64;
   const int rows_per = (hw + chunks - 1) / chunks;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  gn_partial_kernel<<<batch * chunks, 256, 0, s>>>(static_cast<const __half*>(src0),
-                                                   static_cast<const __half*>(src1), c0, c1, hw, rows_per, chunks,
-                                                   scratch);
+  if (src_is_f32)
+    gn_partial_kernel<float><<<batch * chunks, 256, 0, s>>>(static_cast<const float*>(src0),
+                                                            static_cast<const float*>(src1), c0, c1, hw, rows_per,
+                                                            chunks, scratch);
+  else
+    gn_partial_kernel<__half><<<batch * chunks, 256, 0, s>>>(static_cast<const __half*>(src0),
+                                                             static_cast<const __half*>(src1), c0, c1, hw, rows_per,
+                                                             chunks, scratch);
   const double count = static_cast<double>(hw) * ((c0 + c1) / 32);
   gn_final_kernel<<<(batch * 32 + 127) / 128, 128, 0, s>>>(scratch, chunks, count, eps, mean, rstd, batch * 32);
   DGQ_RETURN_LAST_ERROR();
@@ -470,7 +488,7 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
                             const float* beta, float eps, int n_out, const dgq_quant_t* q, void* const* out,
                             uint8_t* const* codes, void* stream) {
   using namespace dgq;
-  DGQ_CHECK_ARG(x != nullptr && m > 0 && c > 0 && c % 8 == 0 && c <= kMaxVecPerLane * 256);
+  DGQ_CHECK_ARG(x != nullptr && m > 0 && c > 0 && c % 8 == 0 && c <= 12 * 256);
   DGQ_CHECK_ARG(n_out >= 1 && n_out <= 3 && q != nullptr && out != nullptr);
   RowQuantDev rq;
   rq.n_out = n_out;
@@ -486,20 +504,29 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
   }
   const int grid = (m + 7) / 8;  // 8 warps (rows) per CTA
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool narrow = c <= 5 * 256;
   if (norm) {
-    DGQ_CHECK_ARG(gamma != nullptr && beta != nullptr && !src_is_f32);
-    row_quant_kernel<__half, true><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, gamma, beta, eps, rq);
+    DGQ_CHECK_ARG(gamma != nullptr && beta != nullptr);
+    if (src_is_f32) {
+      if (narrow) row_quant_kernel<float, true, 5><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, gamma, beta, eps, rq);
+      else row_quant_kernel<float, true, 12><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, gamma, beta, eps, rq);
+    } else {
+      if (narrow) row_quant_kernel<__half, true, 5><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, gamma, beta, eps, rq);
+      else row_quant_kernel<__half, true, 12><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, gamma, beta, eps, rq);
+    }
   } else if (src_is_f32) {
-    row_quant_kernel<float, false><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, nullptr, nullptr, 0.f, rq);
+    if (narrow) row_quant_kernel<float, false, 5><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, nullptr, nullptr, 0.f, rq);
+    else row_quant_kernel<float, false, 12><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, nullptr, nullptr, 0.f, rq);
   } else {
-    row_quant_kernel<__half, false><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, nullptr, nullptr, 0.f, rq);
+    if (narrow) row_quant_kernel<__half, false, 5><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, nullptr, nullptr, 0.f, rq);
+    else row_quant_kernel<__half, false, 12><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, nullptr, nullptr, 0.f, rq);
   }
   DGQ_RETURN_LAST_ERROR();
 }
 
-extern "C" int dgq_ln_quant(const void* x, int m, int c, const float* gamma, const float* beta, float eps,
-                            int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream) {
-  return launch_row_quant(x, 0, true, m, c, gamma, beta, eps, n_out, host_q, host_out, nullptr, stream);
+extern "C" int dgq_ln_quant(const void* x, int src_is_f32, int m, int c, const float* gamma, const float* beta,
+                            float eps, int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream) {
+  return launch_row_quant(x, src_is_f32, true, m, c, gamma, beta, eps, n_out, host_q, host_out, nullptr, stream);
 }
 extern "C" int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_out, const dgq_quant_t* host_q,
                              void* const* host_out, uint8_t* const* host_codes, void* stream) {
@@ -507,26 +534,35 @@ extern "C" int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_
                           stream);
 }
 
-extern "C" int dgq_geglu_quant(const void* x, int m, int f, dgq_quant_t q, void* out, void* stream) {
+extern "C" int dgq_geglu_quant(const void* x, int src_is_f32, int m, int f, dgq_quant_t q, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && m > 0 && f > 0 && f % 8 == 0 && quant_ok(q));
   const int64_t total = static_cast<int64_t>(m) * (f / 8);
-  geglu_quant_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), m, f, to_dev(q), static_cast<__half*>(out));
+  const int grid = grid_for(total, 256, kNumSMs * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_is_f32)
+    geglu_quant_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, f, to_dev(q), static_cast<__half*>(out));
+  else
+    geglu_quant_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, f, to_dev(q), static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }
 
-extern "C" int dgq_qkv_pack(const void* x, int ldx, int b, int t, int heads, int d, int dp, int tp, int transpose,
-                            int skip_first, dgq_quant_t q, void* out, void* stream) {
+extern "C" int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t, int heads, int d, int dp, int tp,
+                            int transpose, int skip_first, dgq_quant_t q, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && t > 0 && heads > 0 && d > 0);
   DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && quant_ok(q));
   DGQ_CHECK_ARG(!transpose || (tp >= t && tp % 8 == 0));
   const int64_t total = transpose ? static_cast<int64_t>(b) * heads * dp * (tp / 8)
                                   : static_cast<int64_t>(b) * heads * t * (dp / 8);
-  qkv_pack_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), ldx, b, t, heads, d, dp, tp, transpose, skip_first, to_dev(q),
-      static_cast<__half*>(out));
+  const int grid = grid_for(total, 256, kNumSMs * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_is_f32)
+    qkv_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), ldx, b, t, heads, d, dp, tp, transpose,
+                                                skip_first, to_dev(q), static_cast<__half*>(out));
+  else
+    qkv_pack_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), ldx, b, t, heads, d, dp, tp,
+                                                 transpose, skip_first, to_dev(q), static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }
 
@@ -540,33 +576,43 @@ extern "C" int dgq_timestep_embedding(const float* t, int n, int dim, void* out_
       t, n, dim, static_cast<__half*>(out_f16), out_f32, ldo);
   DGQ_RETURN_LAST_ERROR();
 }
-extern "C" int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, void* stream) {
+extern "C" int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, int out_is_f32,
+                                void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && c > 0 && hw > 0 && c_pad >= c);
   const int64_t total = static_cast<int64_t>(b) * hw * c_pad;
-  nchw_to_nhwc_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, b, c, hw, c_pad, static_cast<__half*>(out));
+  const int grid = grid_for(total, 256, kNumSMs * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (out_is_f32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(x, b, c, hw, c_pad, static_cast<float*>(out));
+  else nchw_to_nhwc_kernel<__half><<<grid, 256, 0, s>>>(x, b, c, hw, c_pad, static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }
-extern "C" int dgq_nhwc_to_nchw(const void* x, int b, int c, int hw, int ldx, float* out, void* stream) {
+extern "C" int dgq_nhwc_to_nchw(const void* x, int src_is_f32, int b, int c, int hw, int ldx, float* out,
+                                void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && c > 0 && hw > 0 && ldx >= c);
   const int64_t total = static_cast<int64_t>(b) * hw * c;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), b, c, hw, ldx, out);
+  const int grid = grid_for(total, 256, kNumSMs * 16);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (src_is_f32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), b, c, hw, ldx, out);
+  else nhwc_to_nchw_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), b, c, hw, ldx, out);
   DGQ_RETURN_LAST_ERROR();
 }
-extern "C" int dgq_silu_f16(const void* x, int64_t n, void* out, void* stream) {
+extern "C" int dgq_silu(const void* x, int is_f32, int64_t n, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && n > 0);
-  silu_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), n, static_cast<__half*>(out));
+  const int grid = grid_for(n, 256, kNumSMs * 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_f32) silu_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), n, static_cast<float*>(out));
+  else silu_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), n, static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }
-extern "C" int dgq_add_f16(const void* a, const void* b, int64_t n, void* out, void* stream) {
+extern "C" int dgq_add(const void* a, const void* b, int is_f32, int64_t n, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(a != nullptr && b != nullptr && out != nullptr && n > 0);
-  add_kernel<<<grid_for(n, 256, kNumSMs * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(a), static_cast<const __half*>(b), n, static_cast<__half*>(out));
+  const int grid = grid_for(n, 256, kNumSMs * 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (is_f32) add_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(a), static_cast<const float*>(b), n, static_cast<float*>(out));
+  else add_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(a), static_cast<const __half*>(b), n, static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }

@@ -17,6 +17,19 @@ from ._lib import Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE, MAP_NONE, MAP_UNIFORM, M
 
 LAUNCHES = 0  # kernels launched through this module (some entry points launch two)
 
+# dtype of activations BETWEEN kernels (GEMM results, residual stream).  fp32 keeps the inputs of
+# every quantizer identical to the reference's to ~1e-6; fp16 halves that traffic but moves ~1 % of
+# the values across a rounding boundary.  Tensor-core operands are fp16 either way.
+ACT_DTYPE = torch.float32
+
+
+def _is32(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 1
+    if t.dtype == torch.float16:
+        return 0
+    raise TypeError(f"activations must be fp16 or fp32, got {t.dtype}")
+
 
 def _count(n: int = 1) -> None:
     global LAUNCHES
@@ -51,16 +64,19 @@ class QParam:
 NOQ = QParam()
 
 
-def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device, *, kperm=None) -> QParam:
+def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device, *, conv: bool = False,
+                     kperm=None) -> QParam:
     """Map a checkpoint (delta, zp) of shape (), (1,1,X) or (1,X,1) to a device QParam
-    (SURVEY.md 8a').  `kperm` re-orders a K-wise table into the GEMM's K order (conv: tap-major)."""
+    (SURVEY.md 8a').  Linear inputs are (B,T,C): the last axis is K, the middle axis is the row.
+    `conv`: the quantizer saw the unfolded (B, C*kh*kw, L) tensor, so the axes swap.  `kperm`
+    re-orders a K-wise table into the GEMM's K order (conv: tap-major)."""
     d, z = _f32(delta, device), _f32(zp, device)
     if d.dim() == 0 or d.numel() == 1 and d.dim() <= 1:
         return QParam(Q_SCALAR, d.reshape(1), z.reshape(1).expand(1).contiguous(), 1, qmax)
     if d.dim() == 3 and d.shape[0] == 1 and d.shape[1] == 1:      # (1,1,X): last axis
-        mode = Q_KWISE
+        mode = Q_ROWWISE if conv else Q_KWISE
     elif d.dim() == 3 and d.shape[0] == 1 and d.shape[2] == 1:    # (1,X,1): middle axis
-        mode = Q_ROWWISE
+        mode = Q_KWISE if conv else Q_ROWWISE
     else:
         raise ValueError(f"unsupported quantizer parameter shape {tuple(d.shape)}")
     d, z = d.reshape(-1), z.reshape(-1).expand(d.numel())
@@ -158,8 +174,8 @@ def gn_stats(src0: torch.Tensor, src1: Optional[torch.Tensor], batch: int, hw: i
     mean = torch.empty(batch, 32, dtype=torch.float32, device=dev)
     rstd = torch.empty(batch, 32, dtype=torch.float32, device=dev)
     scratch = torch.empty(batch * 64 * 64, dtype=torch.float32, device=dev)
-    L.check(L.lib().dgq_gn_stats(_p(src0), _p(src1), c0, c1, batch, hw, eps, _p(mean), _p(rstd), _p(scratch),
-                                 _stream()), "dgq_gn_stats")
+    L.check(L.lib().dgq_gn_stats(_p(src0), _p(src1), _is32(src0), c0, c1, batch, hw, eps, _p(mean), _p(rstd),
+                                 _p(scratch), _stream()), "dgq_gn_stats")
     _count(2)
     return mean, rstd
 
@@ -175,8 +191,8 @@ def _row_outputs(x, qs):
 def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, qs: Sequence[QParam]):
     """x fp16 [m, c] -> [fp16 [m, c]] * len(qs)."""
     outs, qarr, oarr = _row_outputs(x, qs)
-    L.check(L.lib().dgq_ln_quant(_p(x), x.shape[0], x.shape[1], _p(gamma), _p(beta), eps, len(qs), qarr, oarr,
-                                 _stream()), "dgq_ln_quant")
+    L.check(L.lib().dgq_ln_quant(_p(x), _is32(x), x.shape[0], x.shape[1], _p(gamma), _p(beta), eps, len(qs), qarr,
+                                 oarr, _stream()), "dgq_ln_quant")
     _count()
     return outs
 
@@ -194,25 +210,32 @@ def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False):
 def geglu_quant(x: torch.Tensor, q: QParam) -> torch.Tensor:
     m, f2 = x.shape
     out = torch.empty(m, f2 // 2, dtype=torch.float16, device=x.device)
-    L.check(L.lib().dgq_geglu_quant(_p(x), m, f2 // 2, q.struct(), _p(out), _stream()), "dgq_geglu_quant")
+    L.check(L.lib().dgq_geglu_quant(_p(x), _is32(x), m, f2 // 2, q.struct(), _p(out), _stream()), "dgq_geglu_quant")
     _count()
     return out
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, temb=None, rows_per_batch: int = 0,
          resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None):
-    """a fp16 [m, lda], b fp16 [n_pad, ldb] -> fp16 [m, n] (n multiple of 8)."""
+    """a fp16 [m, lda], b fp16 [n_pad, ldb] -> [m, n] (n multiple of 8), fp32 if want_f32 (or `out`
+    is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32)."""
     m = a.shape[0]
     k = k or min(a.shape[1], b.shape[1])
-    if out is None and not want_f32:
-        out = torch.empty(m, n, dtype=torch.float16, device=a.device)
-    out32 = torch.empty(m, n, dtype=torch.float32, device=a.device) if want_f32 else None
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32 if want_f32 else torch.float16, device=a.device)
+    o32 = out.dtype == torch.float32
+    ep32 = 0
+    for e in (temb, resid):
+        if e is not None:
+            ep32 = _is32(e)
+    if temb is not None and resid is not None and _is32(temb) != _is32(resid):
+        raise TypeError("temb and resid must have the same dtype")
     g = L.GemmT(_p(a), a.stride(0), _p(b), b.stride(0), m, n, k, _p(scale), _p(bias), _p(temb), rows_per_batch,
                 temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
-                _p(out), n, _p(out32))
+                None if o32 else _p(out), out.stride(0), _p(out) if o32 else None, ep32)
     L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
     _count()
-    return out32 if want_f32 else out
+    return out
 
 
 def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, transpose: bool = False,
@@ -220,29 +243,31 @@ def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, tr
     tp = (t + 7) // 8 * 8
     shape = (b, heads, dp, tp) if transpose else (b, heads, t, dp)
     out = torch.empty(shape, dtype=torch.float16, device=x.device)
-    L.check(L.lib().dgq_qkv_pack(_p(x), x.stride(0), b, t, heads, d, dp, tp, int(transpose), int(skip_first),
-                                 q.struct(), _p(out), _stream()), "dgq_qkv_pack")
+    L.check(L.lib().dgq_qkv_pack(_p(x), _is32(x), x.stride(-2), b, t, heads, d, dp, tp, int(transpose),
+                                 int(skip_first), q.struct(), _p(out), _stream()), "dgq_qkv_pack")
     _count()
     return out
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map_mode: int, real_time: bool = False,
               start_peak: bool = False, delta: Optional[torch.Tensor] = None, qmax: float = 255.0,
-              out: Optional[torch.Tensor] = None):
-    """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta)."""
+              out: Optional[torch.Tensor] = None, want_codes: bool = False, out_dtype=torch.float16):
+    """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta[, codes])."""
     b, heads, t, dp = q.shape
     s, sp = k.shape[2], vt.shape[3]
     dev = q.device
     if out is None:
-        out = torch.empty(b * t, heads * d, dtype=torch.float16, device=dev)
+        out = torch.empty(b * t, heads * d, dtype=out_dtype, device=dev)
     row_max = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
     row_sum = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
     gmax = torch.zeros(1 + 1024, dtype=torch.float32, device=dev)
+    codes = torch.zeros(b, heads, t, s, dtype=torch.uint8, device=dev) if want_codes else None
     a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
-                int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0))
+                int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0),
+                _is32(out), _p(codes))
     L.check(L.lib().dgq_attention(C.byref(a), _stream()), "dgq_attention")
-    _count(3)
-    return out, gmax[:1]
+    _count(2)
+    return (out, gmax[:1], codes) if want_codes else (out, gmax[:1])
 
 
 def timestep_embedding(t: torch.Tensor, dim: int, *, f32: bool = False) -> torch.Tensor:
@@ -255,30 +280,34 @@ def timestep_embedding(t: torch.Tensor, dim: int, *, f32: bool = False) -> torch
     return out
 
 
-def nchw_to_nhwc(x: torch.Tensor, c_pad: int) -> torch.Tensor:
+def nchw_to_nhwc(x: torch.Tensor, c_pad: int, dtype=None) -> torch.Tensor:
     b, c, h, w = x.shape
-    out = torch.empty(b, h, w, c_pad, dtype=torch.float16, device=x.device)
-    L.check(L.lib().dgq_nchw_to_nhwc(_p(x.contiguous()), b, c, h * w, c_pad, _p(out), _stream()), "dgq_nchw_to_nhwc")
+    out = torch.empty(b, h, w, c_pad, dtype=dtype or ACT_DTYPE, device=x.device)
+    x = x.contiguous()
+    L.check(L.lib().dgq_nchw_to_nhwc(_p(x), b, c, h * w, c_pad, _p(out), _is32(out), _stream()), "dgq_nchw_to_nhwc")
     _count()
     return out
 
 
 def nhwc_to_nchw(x: torch.Tensor, b: int, c: int, h: int, w: int) -> torch.Tensor:
     out = torch.empty(b, c, h, w, dtype=torch.float32, device=x.device)
-    L.check(L.lib().dgq_nhwc_to_nchw(_p(x), b, c, h * w, x.stride(-2), _p(out), _stream()), "dgq_nhwc_to_nchw")
+    L.check(L.lib().dgq_nhwc_to_nchw(_p(x), _is32(x), b, c, h * w, x.stride(-2), _p(out), _stream()),
+            "dgq_nhwc_to_nchw")
     _count()
     return out
 
 
 def silu(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(x)
-    L.check(L.lib().dgq_silu_f16(_p(x), x.numel(), _p(out), _stream()), "dgq_silu_f16")
+    L.check(L.lib().dgq_silu(_p(x), _is32(x), x.numel(), _p(out), _stream()), "dgq_silu")
     _count()
     return out
 
 
 def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(a)
-    L.check(L.lib().dgq_add_f16(_p(a), _p(b), a.numel(), _p(out), _stream()), "dgq_add_f16")
+    if a.dtype != b.dtype:
+        raise TypeError("add: dtype mismatch")
+    L.check(L.lib().dgq_add(_p(a), _p(b), _is32(a), a.numel(), _p(out), _stream()), "dgq_add")
     _count()
     return out

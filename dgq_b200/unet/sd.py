@@ -1,0 +1,106 @@
+"""Stable Diffusion v1.4 UNet graph -- same module tree and parameter names as the reference's
+diffusers_rewrite/sd.py (:493-544), executed by dgq_b200.engine."""
+import torch.nn as nn
+
+from .common import (Attention, Downsample2D, FeedForward, GEGLU, ResnetBlock2D, TimestepEmbedding,
+                     Timesteps, Upsample2D, BasicTransformerBlockBase, Transformer2DModelBase, _BlockList,
+                     UNetBase)
+from .. import engine
+
+__all__ = ["Timesteps", "TimestepEmbedding", "ResnetBlock2D", "Attention", "GEGLU", "FeedForward",
+           "BasicTransformerBlock", "Transformer2DModel", "Downsample2D", "Upsample2D", "DownBlock2D",
+           "CrossAttnDownBlock2D", "CrossAttnUpBlock2D", "UpBlock2D", "UNetMidBlock2DCrossAttn",
+           "UNet2DConditionModel"]
+
+
+class BasicTransformerBlock(BasicTransformerBlockBase):
+    def __init__(self, hidden_size):
+        super().__init__(hidden_size, 768, num_heads=8)
+
+
+class Transformer2DModel(Transformer2DModelBase):
+    def __init__(self, in_channels, out_channels, n_layers):
+        super().__init__()
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-06, affine=True)
+        self.proj_in = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(out_channels) for _ in range(n_layers)])
+        self.proj_out = nn.Conv2d(out_channels, out_channels, kernel_size=1, stride=1)
+
+
+class DownBlock2D(_BlockList):
+    def __init__(self, in_channels, out_channels, has_downsamplers=True):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels, out_channels, conv_shortcut=False),
+                                      ResnetBlock2D(out_channels, out_channels, conv_shortcut=False)])
+        self.downsamplers = None
+        if has_downsamplers:
+            self.downsamplers = nn.ModuleList([Downsample2D(out_channels, out_channels)])
+
+
+class CrossAttnDownBlock2D(_BlockList):
+    def __init__(self, in_channels, out_channels, n_layers, has_downsamplers=True, has_shortcut=True):
+        super().__init__()
+        self.attentions = nn.ModuleList([Transformer2DModel(out_channels, out_channels, n_layers),
+                                         Transformer2DModel(out_channels, out_channels, n_layers)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels, out_channels, conv_shortcut=has_shortcut),
+                                      ResnetBlock2D(out_channels, out_channels, conv_shortcut=False)])
+        self.downsamplers = None
+        if has_downsamplers:
+            self.downsamplers = nn.ModuleList([Downsample2D(out_channels, out_channels)])
+
+
+class CrossAttnUpBlock2D(_BlockList):
+    def __init__(self, in_channels, out_channels, prev_output_channel, n_layers, has_upsamplers=True):
+        super().__init__()
+        self.attentions = nn.ModuleList([Transformer2DModel(out_channels, out_channels, n_layers) for _ in range(3)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(prev_output_channel + out_channels, out_channels),
+                                      ResnetBlock2D(2 * out_channels, out_channels),
+                                      ResnetBlock2D(out_channels + in_channels, out_channels)])
+        self.upsamplers = None
+        if has_upsamplers:
+            self.upsamplers = nn.ModuleList([Upsample2D(out_channels, out_channels)])
+
+
+class UpBlock2D(_BlockList):
+    def __init__(self, in_channels, out_channels, prev_output_channel):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(out_channels + prev_output_channel, out_channels),
+                                      ResnetBlock2D(out_channels * 2, out_channels),
+                                      ResnetBlock2D(out_channels + in_channels, out_channels)])
+        self.upsamplers = nn.ModuleList([Upsample2D(out_channels, out_channels)])
+
+
+class UNetMidBlock2DCrossAttn(_BlockList):
+    def __init__(self, in_features):
+        super().__init__()
+        self.attentions = nn.ModuleList([Transformer2DModel(in_features, in_features, n_layers=1)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_features, in_features, conv_shortcut=False),
+                                      ResnetBlock2D(in_features, in_features, conv_shortcut=False)])
+
+
+class UNet2DConditionModel(UNetBase):
+    def __init__(self):
+        super().__init__()
+        self.register_to_config(in_channels=4, sample_size=64, time_cond_proj_dim=None)
+        self.conv_in = nn.Conv2d(4, 320, kernel_size=3, stride=1, padding=1)
+        self.time_proj = Timesteps()
+        self.time_embedding = TimestepEmbedding(in_features=320, out_features=1280)
+        self.down_blocks = nn.ModuleList([
+            CrossAttnDownBlock2D(in_channels=320, out_channels=320, n_layers=1, has_shortcut=False),
+            CrossAttnDownBlock2D(in_channels=320, out_channels=640, n_layers=1, has_shortcut=True),
+            CrossAttnDownBlock2D(in_channels=640, out_channels=1280, n_layers=1, has_shortcut=True),
+            DownBlock2D(in_channels=1280, out_channels=1280, has_downsamplers=False)])
+        self.up_blocks = nn.ModuleList([
+            UpBlock2D(in_channels=1280, out_channels=1280, prev_output_channel=1280),
+            CrossAttnUpBlock2D(in_channels=640, out_channels=1280, prev_output_channel=1280, n_layers=1),
+            CrossAttnUpBlock2D(in_channels=320, out_channels=640, prev_output_channel=1280, n_layers=1),
+            CrossAttnUpBlock2D(in_channels=320, out_channels=320, prev_output_channel=640, n_layers=1,
+                               has_upsamplers=False)])
+        self.mid_block = UNetMidBlock2DCrossAttn(1280)
+        self.conv_norm_out = nn.GroupNorm(32, 320, eps=1e-05, affine=True)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(320, 4, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, sample, timesteps, encoder_hidden_states=None, **kwargs):
+        # extra pipeline kwargs (timestep_cond, cross_attention_kwargs, return_dict, ...) are swallowed
+        return [engine.unet_forward(self, sample, timesteps, encoder_hidden_states)]

@@ -11,8 +11,12 @@
  *     nothing synchronises;
  *   - return value: 0 on success, a positive cudaError_t, or DGQ_ERR_INVALID_VALUE (-1) when an
  *     argument violates a documented constraint.  Nothing throws across the boundary;
- *   - activations are fp16 ("half"), token-major / NHWC: a tensor (B, H, W, C) or (B, T, C) is a
- *     row-major matrix [M = B*H*W, C]; scales are fp32.
+ *   - activations are token-major / NHWC: a tensor (B, H, W, C) or (B, T, C) is a row-major
+ *     matrix [M = B*H*W, C].  Tensor-core OPERANDS (quantised activations, weights, Q/K/V, the
+ *     softmax map) are fp16; the activations BETWEEN kernels (GEMM results, residual stream) are
+ *     fp32 by default, because every one of them feeds a quantizer and fp16 storage alone moves
+ *     ~1 % of the values across a rounding boundary (DESIGN.md "why fp32 between kernels");
+ *     `*_is_f32` flags select fp16 storage instead.  Scales are fp32.
  */
 #ifndef DGQ_B200_H_
 #define DGQ_B200_H_
@@ -96,14 +100,14 @@ int dgq_act_producer(const dgq_producer_t* host_args, void* stream);
 
 /* GroupNorm(32, C) statistics over a (two-source) NHWC fp16 tensor -> mean, rstd [batch, 32].
  * scratch: >= batch * 64 * 64 floats.                                                         */
-int dgq_gn_stats(const void* src0, const void* src1, int c0, int c1, int batch, int hw, float eps,
-                 float* mean, float* rstd, float* scratch, void* stream);
+int dgq_gn_stats(const void* src0, const void* src1, int src_is_f32, int c0, int c1, int batch, int hw,
+                 float eps, float* mean, float* rstd, float* scratch, void* stream);
 
 /* LayerNorm(C, eps) + up to three UniformAffineQuantizers of the same normalised row
  * (norm1 -> to_q/to_k/to_v, diffusers_rewrite/sd.py:252-269; quant/quant_layer.py:640-641).
- * x: fp16 [m, c]; out[i]: fp16 [m, c].                                                         */
-int dgq_ln_quant(const void* x, int m, int c, const float* gamma, const float* beta, float eps,
-                 int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream);
+ * x: fp16/fp32 [m, c]; out[i]: fp16 [m, c].                                                    */
+int dgq_ln_quant(const void* x, int src_is_f32, int m, int c, const float* gamma, const float* beta,
+                 float eps, int n_out, const dgq_quant_t* host_q, void* const* host_out, void* stream);
 
 /* row quantizer without a norm (cross-attention to_k/to_v on encoder_hidden_states, fp32 or fp16
  * input [m, c]) -- same outputs as dgq_ln_quant                                                */
@@ -111,8 +115,8 @@ int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_out, const 
                   void* const* host_out, uint8_t* const* host_codes, void* stream);
 
 /* GEGLU (diffusers_rewrite/sd.py:215-218: x1 * gelu_erf(x2)) + quantizer of ff.net.2.
- * x: fp16 [m, 2f] -> out fp16 [m, f]                                                            */
-int dgq_geglu_quant(const void* x, int m, int f, dgq_quant_t q, void* out, void* stream);
+ * x: fp16/fp32 [m, 2f] -> out fp16 [m, f]                                                       */
+int dgq_geglu_quant(const void* x, int src_is_f32, int m, int f, dgq_quant_t q, void* out, void* stream);
 
 /* ---- qGEMM: C[m, n] = (A[m, k] . B[n, k]^T) * scale[n] + bias[n] (+ temb[m / rows_per_batch, n])
  *      (+ resid[m, n]) on tcgen05/TMEM, TMA-fed (replaces F.linear / F.conv2d / W.view(Co,-1) @ x_unf,
@@ -125,12 +129,13 @@ typedef struct {
   int m, n, k;
   const float* scale;  /* [n] per-out-channel weight delta, or NULL (=1) */
   const float* bias;   /* [n] or NULL */
-  const void* temb;    /* fp16 [m / rows_per_batch, ld_temb] or NULL */
+  const void* temb;    /* [m / rows_per_batch, ld_temb] or NULL; fp32 when ep_is_f32 else fp16 */
   int rows_per_batch, ld_temb;
-  const void* resid;   /* fp16 [m, ld_resid] or NULL */
+  const void* resid;   /* [m, ld_resid] or NULL; fp32 when ep_is_f32 else fp16 */
   int ld_resid;
-  void* out; int ldc;  /* fp16 */
-  float* out_f32;      /* optional fp32 copy of the result */
+  void* out; int ldc;  /* fp16 result, optional */
+  float* out_f32;      /* fp32 result, optional (at least one of out / out_f32) */
+  int ep_is_f32;       /* dtype of temb / resid */
 } dgq_gemm_t;
 int dgq_gemm_f16(const dgq_gemm_t* host_args, void* stream);
 
@@ -141,7 +146,7 @@ int dgq_gemm_f16(const dgq_gemm_t* host_args, void* stream);
  *   transpose == 1: out fp16 [b, heads, dp, tp]        (V^T), tp = round_up(t, 8)
  *   q.mode: NONE / SCALAR / KWISE (index d) / ROWWISE (index t - skip_first).
  *   skip_first == 1: token 0 bypasses the quantizer (start-peak, sd.py:176-180).               */
-int dgq_qkv_pack(const void* x, int ldx, int b, int t, int heads, int d, int dp, int tp,
+int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t, int heads, int d, int dp, int tp,
                  int transpose, int skip_first, dgq_quant_t q, void* out, void* stream);
 
 #define DGQ_MAP_NONE 0    /* use_aq off: plain softmax                                   */
@@ -161,8 +166,10 @@ typedef struct {
   float* row_max;       /* scratch [b*heads*t] */
   float* row_sum;       /* scratch [b*heads*t] */
   float* gmax;          /* scratch [1 + 1024]; gmax[0] receives the real-time delta */
-  void* out;            /* fp16 [b*t, ldo], head h at columns h*d .. h*d+d-1 */
+  void* out;            /* [b*t, ldo], head h at columns h*d .. h*d+d-1; fp32 when out_is_f32 */
   int ldo;
+  int out_is_f32;
+  uint8_t* codes;       /* optional u8 [b, heads, t, s]: integer codes of the map (verification only) */
 } dgq_attn_t;
 int dgq_attention(const dgq_attn_t* host_args, void* stream);
 
@@ -170,13 +177,13 @@ int dgq_attention(const dgq_attn_t* host_args, void* stream);
 /* Timesteps.forward (diffusers_rewrite/sd.py:25-39): [n] fp32 -> fp16/fp32 [n, dim] (cos | sin) */
 int dgq_timestep_embedding(const float* t, int n, int dim, void* out_f16, float* out_f32, int ldo,
                            void* stream);
-/* fp32 NCHW -> fp16 NHWC with channel padding (conv_in input), and back (conv_out result)       */
-int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, void* stream);
-int dgq_nhwc_to_nchw(const void* x, int b, int c, int hw, int ldx, float* out, void* stream);
-/* y = act(x) elementwise on fp16 (SiLU on the time embedding, quant/quant_block.py:107)        */
-int dgq_silu_f16(const void* x, int64_t n, void* out, void* stream);
-/* out = a + b (fp16)                                                                            */
-int dgq_add_f16(const void* a, const void* b, int64_t n, void* out, void* stream);
+/* fp32 NCHW -> fp16/fp32 NHWC with channel padding (conv_in input), and back (conv_out result)  */
+int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out, int out_is_f32, void* stream);
+int dgq_nhwc_to_nchw(const void* x, int src_is_f32, int b, int c, int hw, int ldx, float* out, void* stream);
+/* y = silu(x) elementwise (SiLU on the time embedding, quant/quant_block.py:107); fp16 or fp32  */
+int dgq_silu(const void* x, int is_f32, int64_t n, void* out, void* stream);
+/* out = a + b; fp16 or fp32                                                                     */
+int dgq_add(const void* a, const void* b, int is_f32, int64_t n, void* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -186,18 +186,11 @@ def _map_quant(m: Tensor, act, name: str, cfg: "QConfig") -> Tensor:
                           act[name + ".aqtizer_w.zero_point"], lv)
 
 
-def attention(x: Tensor, ctx: Optional[Tensor], sd, act, name: str, cfg: QConfig, *,
-              heads: int, is_cross: bool, return_probs: bool = False) -> Tensor:
-    """Attention.Attention_forward (diffusers_rewrite/sd.py:151-207, sdxl.py:174-229)."""
-    src = ctx if ctx is not None else x
-    q = quant_layer(x, sd, act, name + ".to_q", cfg)
-    k = quant_layer(src, sd, act, name + ".to_k", cfg)
-    v = quant_layer(src, sd, act, name + ".to_v", cfg)
-    b, t, c = q.shape
-    d = c // heads
-    q = q.view(b, -1, heads, d).transpose(1, 2)
-    k = k.view(b, -1, heads, d).transpose(1, 2)
-    v = v.view(b, -1, heads, d).transpose(1, 2)
+def attention_core(q: Tensor, k: Tensor, v: Tensor, act, name: str, cfg: QConfig, *, is_cross: bool,
+                   return_probs: bool = False) -> Tensor:
+    """The part of Attention_forward between the projections (sd.py:171-201): q, k, v are
+    (B, H, T, D); returns (B, T, H*D)."""
+    b, heads, t, d = q.shape
     start_peak = cfg.t2i_start_peak and is_cross  # quant_block.py:157-158
     level = 2 ** cfg.abits
     if cfg.use_aq:
@@ -210,7 +203,6 @@ def attention(x: Tensor, ctx: Optional[Tensor], sd, act, name: str, cfg: QConfig
     p = torch.softmax(scores, dim=-1)
     if cfg.use_aq:  # sd.py:187-199
         p = p.float()
-
         if start_peak:
             p = torch.cat([p[..., 0:1], _map_quant(p[..., 1:], act, name, cfg)], dim=-1)
         else:
@@ -218,7 +210,22 @@ def attention(x: Tensor, ctx: Optional[Tensor], sd, act, name: str, cfg: QConfig
         v = _aq(act, name + ".aqtizer_v", v, level)
     if return_probs:
         return p
-    o = torch.matmul(p, v).transpose(1, 2).contiguous().view(b, t, c)
+    return torch.matmul(p, v).transpose(1, 2).contiguous().view(b, t, heads * d)
+
+
+def attention(x: Tensor, ctx: Optional[Tensor], sd, act, name: str, cfg: QConfig, *,
+              heads: int, is_cross: bool) -> Tensor:
+    """Attention.Attention_forward (diffusers_rewrite/sd.py:151-207, sdxl.py:174-229)."""
+    src = ctx if ctx is not None else x
+    q = quant_layer(x, sd, act, name + ".to_q", cfg)
+    k = quant_layer(src, sd, act, name + ".to_k", cfg)
+    v = quant_layer(src, sd, act, name + ".to_v", cfg)
+    b, t, c = q.shape
+    d = c // heads
+    q = q.view(b, -1, heads, d).transpose(1, 2)
+    k = k.view(b, -1, heads, d).transpose(1, 2)
+    v = v.view(b, -1, heads, d).transpose(1, 2)
+    o = attention_core(q, k, v, act, name, cfg, is_cross=is_cross)
     return quant_layer(o, sd, act, name + ".to_out.0", cfg)
 
 
@@ -316,7 +323,7 @@ SPECS = {"sd": SD_SPEC, "sdxl": SDXL_SPEC}
 
 
 def unet_forward(model_type: str, sd, act, cfg: QConfig, sample: Tensor, timesteps: Tensor,
-                 ctx: Tensor, added: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                 ctx: Tensor, added: Optional[Dict[str, Tensor]] = None, taps: Optional[list] = None) -> Tensor:
     """UNet2DConditionModel.forward (sd.py:546-620, sdxl.py:558-631) behind
     QuantModel.forward (quant/quant_model.py:113-116)."""
     spec = SPECS[model_type]
@@ -331,14 +338,22 @@ def unet_forward(model_type: str, sd, act, cfg: QConfig, sample: Tensor, timeste
         add = torch.cat([added["text_embeds"], te], dim=-1).to(emb.dtype)
         emb = emb + _time_mlp(add, sd, act, P + "add_embedding", cfg)
 
+    def tap(name, x):
+        if taps is not None:
+            taps.append((name, x.detach().clone()))
+
+    tap("emb", emb)
     h = quant_layer(sample, sd, act, P + "conv_in", cfg, padding=1, fp_layer=True)
+    tap("conv_in", h)
     skips = [h]
     for i, (cin, cout, nl, has_down) in enumerate(spec["down"]):
         for j in range(2):
             h = resnet(h, emb, sd, act, f"{P}down_blocks.{i}.resnets.{j}", cfg)
+            tap(f"down{i}.res{j}", h)
             if nl is not None:
                 h = transformer2d(h, ctx, sd, act, f"{P}down_blocks.{i}.attentions.{j}", cfg,
                                   n_layers=nl, heads=heads(cout), linear_proj=lp)
+                tap(f"down{i}.attn{j}", h)
             skips.append(h)
         if has_down:
             h = quant_layer(h, sd, act, f"{P}down_blocks.{i}.downsamplers.0.conv", cfg, stride=2, padding=1)
@@ -348,14 +363,17 @@ def unet_forward(model_type: str, sd, act, cfg: QConfig, sample: Tensor, timeste
     h = transformer2d(h, ctx, sd, act, P + "mid_block.attentions.0", cfg,
                       n_layers=spec["mid_layers"], heads=heads(1280), linear_proj=lp)
     h = resnet(h, emb, sd, act, P + "mid_block.resnets.1", cfg)
+    tap("mid", h)
 
     for i, (cin, cout, prev, nl, has_up) in enumerate(spec["up"]):
         for j in range(3):
             h = torch.cat([h, skips.pop()], dim=1)
             h = resnet(h, emb, sd, act, f"{P}up_blocks.{i}.resnets.{j}", cfg)
+            tap(f"up{i}.res{j}", h)
             if nl is not None:
                 h = transformer2d(h, ctx, sd, act, f"{P}up_blocks.{i}.attentions.{j}", cfg,
                                   n_layers=nl, heads=heads(cout), linear_proj=lp)
+                tap(f"up{i}.attn{j}", h)
         if has_up:
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = quant_layer(h, sd, act, f"{P}up_blocks.{i}.upsamplers.0.conv", cfg, padding=1)

@@ -5,7 +5,7 @@ copy):
 
     python tests/golden/make_golden.py ops          # op-level vectors  -> ops.pt
     python tests/golden/make_golden.py unet sd      # full-UNet latents -> unet_sd_*.pt
-    python tests/golden/make_golden.py unet sdxl
+    python tests/golden/make_golden.py unet sdxl [case]   # one case per process keeps peak RSS < 60 GB
 
 Inputs are regenerated from seeds by the tests (oracle/synth.py uses numpy
 PCG64 / torch CPU generators, both machine-independent), so only the
@@ -232,13 +232,15 @@ def build_case(S, O, model_type, case, torch):
     return sd, cfg, acts
 
 
-def make_unet(model_type):
+def make_unet(model_type, only=None):
     torch, O, S = import_reference(model_type)
     import diffusers_rewrite
     from quant.quant_layer import Scaler
     from quant.load_qmodel_util import get_qmodel
     import time
     for case in UNET_RUNS[model_type]:
+        if only is not None and case != only:
+            continue
         wb, ab, gn, log, rt, sp, n_steps, batch, ts = UNET_CASES[case]
         t0 = time.time()
         sd, cfg, acts = build_case(S, O, model_type, case, torch)
@@ -284,4 +286,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "ops":
         make_ops()
     else:
-        make_unet(sys.argv[2])
+        make_unet(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

@@ -130,12 +130,7 @@ def test_act_producer_codes_bit_exact(k, s, ci, hw, mode):
     codes_ref, dq_ref = _unfold_ref(x, k, s, d, z, grouped)
     # reference K order c*k*k + tap -> ours tap*C + c
     kperm = (torch.arange(ci).view(1, ci) * (k * k) + torch.arange(k * k).view(k * k, 1)).reshape(-1)
-    if mode == "kwise":
-        q = ops.qparam_from_ckpt(d.view(1, 1, -1), z.view(1, 1, -1), 255.0, DEV, kperm=kperm)
-    elif mode == "rowwise":
-        q = ops.qparam_from_ckpt(d.view(1, -1, 1), z.view(1, -1, 1), 255.0, DEV)
-    else:
-        q = ops.qparam_from_ckpt(d, z, 255.0, DEV)
+    q = ops.qparam_from_ckpt(d, z, 255.0, DEV, conv=True, kperm=kperm)  # checkpoint-shaped (1,X,1)/(1,1,X)
     xin = x.permute(0, 2, 3, 1).contiguous().to(DEV)
     out, codes = ops.act_producer(xin, batch=bsz, h=hw, w=hw, ksize=k, stride=s, q=q, pad_quantized=grouped,
                                   want_codes=True)
@@ -204,7 +199,7 @@ def test_config1_quant_layer(ops_golden, mode):
     layer = torch.nn.Conv2d(320, 320, 3, 1, 1)
     x = torch.randn(1, 320, 64, 64, generator=g)
     kperm = (torch.arange(320).view(1, 320) * 9 + torch.arange(9).view(9, 1)).reshape(-1)
-    q = ops.qparam_from_ckpt(c["delta"], c["zp"], 255.0, DEV, kperm=kperm)
+    q = ops.qparam_from_ckpt(c["delta"], c["zp"], 255.0, DEV, conv=True, kperm=kperm)
     operand, _, _ = ops.pack_weight(layer.weight.detach().to(DEV), c["wdelta"], c["wzp"], None, 15.0, True)
     a = ops.act_producer(x.permute(0, 2, 3, 1).contiguous().to(DEV), batch=1, h=64, w=64, ksize=3, q=q,
                          pad_quantized=c["grouped"])
@@ -288,7 +283,7 @@ def test_glue_kernels():
     e = ops.timestep_embedding(t.to(DEV), 320, f32=True)
     assert torch.allclose(e.cpu(), O.timestep_embedding(t, 320), atol=2e-4)
     x = torch.randn(2, 4, 8, 8)
-    y = ops.nchw_to_nhwc(x.to(DEV), 8)
+    y = ops.nchw_to_nhwc(x.to(DEV), 8, dtype=torch.float16)
     assert torch.equal(y.cpu()[..., :4].float(), x.permute(0, 2, 3, 1).half().float())
     assert (y.cpu()[..., 4:] == 0).all()
     z = ops.nhwc_to_nchw(y, 2, 4, 8, 8)
