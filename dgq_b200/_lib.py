@@ -21,7 +21,7 @@ MAP_NONE, MAP_UNIFORM, MAP_LOG2 = 0, 1, 2
 
 class QuantT(C.Structure):
     _fields_ = [("delta", C.c_void_p), ("zp", C.c_void_p), ("mode", C.c_int), ("period", C.c_int),
-                ("qmax", C.c_float)]
+                ("qmax", C.c_float), ("emit_int", C.c_int)]
 
 
 class ProducerT(C.Structure):
@@ -36,7 +36,7 @@ class ProducerT(C.Structure):
 class GemmT(C.Structure):
     _fields_ = [("a", C.c_void_p), ("lda", C.c_int), ("b", C.c_void_p), ("ldb", C.c_int),
                 ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("scale", C.c_void_p),
-                ("bias", C.c_void_p), ("temb", C.c_void_p), ("rows_per_batch", C.c_int),
+                ("row_scale", C.c_void_p), ("row_period", C.c_int), ("bias", C.c_void_p), ("temb", C.c_void_p), ("rows_per_batch", C.c_int),
                 ("ld_temb", C.c_int), ("resid", C.c_void_p), ("ld_resid", C.c_int),
                 ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p), ("ep_is_f32", C.c_int)]
 

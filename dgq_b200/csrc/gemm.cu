@@ -34,6 +34,8 @@ struct GemmDev {
   int m, n, k, bn;
   int m_tiles, n_tiles;
   const float* scale;
+  const float* row_scale;
+  int row_period;
   const float* bias;
   const void* temb;
   int rows_per_batch, ld_temb;
@@ -144,6 +146,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const char* resid_row = (p.resid != nullptr && row_ok)
                                   ? static_cast<const char*>(p.resid) + static_cast<size_t>(row) * p.ld_resid * esz
                                   : nullptr;
+      const float rs = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
       const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = 0; c < p.bn; c += 32) {
         uint32_t r[32];
@@ -157,7 +160,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (n < p.n) {
               float f[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]);
+              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]) * rs;
               if (p.scale != nullptr) {
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n));
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n + 4));
@@ -276,6 +279,7 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   p.m_tiles = (a->m + kBM - 1) / kBM;
   p.n_tiles = (a->n + p.bn - 1) / p.bn;
   p.scale = a->scale; p.bias = a->bias;
+  p.row_scale = a->row_scale; p.row_period = a->row_period > 0 ? a->row_period : 1;
   p.temb = a->temb;
   p.rows_per_batch = a->rows_per_batch; p.ld_temb = a->ld_temb;
   p.resid = a->resid; p.ld_resid = a->ld_resid;

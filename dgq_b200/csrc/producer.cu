@@ -21,9 +21,12 @@ struct QuantDev {
   int mode;
   int period;
   float qmax;
+  int emit_int;
 };
 
-static QuantDev to_dev(const dgq_quant_t& q) { return QuantDev{q.delta, q.zp, q.mode, q.period, q.qmax}; }
+static QuantDev to_dev(const dgq_quant_t& q) {
+  return QuantDev{q.delta, q.zp, q.mode, q.period, q.qmax, q.emit_int};
+}
 
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
@@ -51,7 +54,7 @@ __device__ __forceinline__ void quant8(const QuantDev& q, float (&v)[8], int k0,
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float c = uaq_code(v[i], d[i], z[i], q.qmax);
-    v[i] = uaq_dequant(c, d[i], z[i]);
+    v[i] = q.emit_int ? __fsub_rn(c, z[i]) : uaq_dequant(c, d[i], z[i]);
     if (i < 4) lo |= static_cast<uint32_t>(c) << (8 * i);
     else hi |= static_cast<uint32_t>(c) << (8 * (i - 4));
   }
@@ -422,6 +425,7 @@ static bool quant_ok(const dgq_quant_t& q) {
   if (q.mode < 0 || q.mode > DGQ_Q_ROWWISE) return false;
   if (q.delta == nullptr || q.zp == nullptr) return false;
   if (q.mode == DGQ_Q_ROWWISE && q.period <= 0) return false;
+  if (q.emit_int && q.mode == DGQ_Q_KWISE) return false;
   return true;
 }
 
@@ -494,7 +498,7 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
   rq.n_out = n_out;
   for (int i = 0; i < 3; ++i) {
     rq.out[i] = nullptr; rq.codes[i] = nullptr;
-    rq.q[i] = QuantDev{nullptr, nullptr, DGQ_Q_NONE, 1, 0.f};
+    rq.q[i] = QuantDev{nullptr, nullptr, DGQ_Q_NONE, 1, 0.f, 0};
   }
   for (int i = 0; i < n_out; ++i) {
     DGQ_CHECK_ARG(out[i] != nullptr && quant_ok(q[i]));
@@ -551,7 +555,7 @@ extern "C" int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t
                             int transpose, int skip_first, dgq_quant_t q, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && t > 0 && heads > 0 && d > 0);
-  DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && quant_ok(q));
+  DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && quant_ok(q) && !q.emit_int);
   DGQ_CHECK_ARG(!transpose || (tp >= t && tp % 8 == 0));
   const int64_t total = transpose ? static_cast<int64_t>(b) * heads * dp * (tp / 8)
                                   : static_cast<int64_t>(b) * heads * t * (dp / 8);

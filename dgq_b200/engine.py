@@ -69,12 +69,23 @@ def act_to_tokens(a: Act, dtype=torch.float32) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # QuantLayer
 # ------------------------------------------------------------------------------------------
-def _gemm(ql, a_op: torch.Tensor, *, temb=None, rows_per_batch=0, resid=None, want_f32=None):
+EXACT_INT = True  # integer A operand + per-row delta in the epilogue wherever the scales allow it
+
+
+def _exact(q: ops.QParam) -> bool:
+    return EXACT_INT and q.exact
+
+
+def _gemm(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, temb=None, rows_per_batch=0, resid=None,
+          want_f32=None):
+    """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q`."""
     operand, scale, bias, n_pad = ql.packed()
     if want_f32 is None:
         want_f32 = ops.ACT_DTYPE == torch.float32
+    ex = _exact(q)
     return ops.gemm(a_op, operand, n_pad, scale=scale, bias=bias, temb=temb, rows_per_batch=rows_per_batch,
-                    resid=resid, want_f32=want_f32, k=operand.shape[1])
+                    resid=resid, want_f32=want_f32, k=operand.shape[1],
+                    row_scale=q.delta if ex else None, row_period=q.period if ex else 1)
 
 
 def conv(ql, x: Act, *, x2: Optional[Act] = None, upsample: bool = False, gn=None, act: int = 0,
@@ -86,15 +97,23 @@ def conv(ql, x: Act, *, x2: Optional[Act] = None, upsample: bool = False, gn=Non
     k, s = ql.ksize, ql.stride
     pad = k // 2
     ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    q = ql.act_qparam(dev)
     a_op = ops.act_producer(x.t, src1=None if x2 is None else x2.t, batch=x.b, h=h, w=w, upsample=upsample,
-                            ksize=k, stride=s, gn=gn, act=act, q=ql.act_qparam(dev),
-                            pad_quantized=ql.pad_quantized)
-    out = _gemm(ql, a_op, temb=temb, rows_per_batch=ho * wo, resid=resid)
+                            ksize=k, stride=s, gn=gn, act=act, q=q, pad_quantized=ql.pad_quantized,
+                            emit_int=_exact(q))
+    out = _gemm(ql, a_op, q, temb=temb, rows_per_batch=ho * wo, resid=resid)
     return Act(out, x.b, ho, wo)
 
 
-def linear(ql, a_op: torch.Tensor, *, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
-    return _gemm(ql, a_op, resid=resid)
+def linear(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qGEMM on an operand produced with emit_int=EXACT_INT under quantizer q (= ql.act_qparam)."""
+    return _gemm(ql, a_op, q, resid=resid)
+
+
+def quant_rows(x: torch.Tensor, ql) -> Tuple[torch.Tensor, ops.QParam]:
+    """quantize rows of x for QuantLayer ql -> (operand, q)"""
+    q = ql.act_qparam(x.device)
+    return ops.row_quant(x, [q], emit_int=EXACT_INT)[0], q
 
 
 def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
@@ -114,10 +133,11 @@ def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
         k, s = ql.ksize, ql.stride
         if q.mode == ops.Q_KWISE and c % 8:
             raise NotImplementedError("K-wise scales need a channel count that is a multiple of 8")
-        a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=k, stride=s, q=q, pad_quantized=ql.pad_quantized)
+        a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=k, stride=s, q=q, pad_quantized=ql.pad_quantized,
+                                emit_int=_exact(q))
         pad = k // 2
         ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
-        y = _gemm(ql, a_op, want_f32=True)
+        y = _gemm(ql, a_op, q, want_f32=True)
         return y[:, :n].reshape(b, ho, wo, n).permute(0, 3, 1, 2).contiguous().to(x.dtype)
     shp = x.shape
     x2 = x.detach().reshape(-1, shp[-1])
@@ -126,8 +146,8 @@ def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
     x2 = x2.contiguous()
     if q.mode == ops.Q_ROWWISE and (x.dim() != 3 or q.period != shp[-2]):
         raise ValueError(f"row-wise scales for {q.period} tokens do not fit an input of shape {tuple(shp)}")
-    a_op = ops.row_quant(x2, [q])[0]
-    y = _gemm(ql, a_op, want_f32=True)
+    a_op = ops.row_quant(x2, [q], emit_int=EXACT_INT)[0]
+    y = _gemm(ql, a_op, q, want_f32=True)
     return y[:, :n].reshape(*shp[:-1], n).to(x.dtype)
 
 
@@ -156,16 +176,15 @@ def _f32(p: torch.Tensor) -> torch.Tensor:
 
 def time_mlp(emb_mod, x: torch.Tensor) -> torch.Tensor:
     """TimestepEmbedding: linear_1 -> SiLU -> linear_2 on [B, C] (2-D inputs: scalar quantizers only)."""
-    dev = x.device
-    h = linear(emb_mod.linear_1, ops.row_quant(x, [emb_mod.linear_1.act_qparam(dev)])[0])
+    h = linear(emb_mod.linear_1, *quant_rows(x, emb_mod.linear_1))
     h = ops.silu(h)
-    return linear(emb_mod.linear_2, ops.row_quant(h, [emb_mod.linear_2.act_qparam(dev)])[0])
+    return linear(emb_mod.linear_2, *quant_rows(h, emb_mod.linear_2))
 
 
 def resnet(blk, x: Act, silu_emb: torch.Tensor, x2: Optional[Act] = None) -> Act:
     """QuantResnetBlock2D.forward (reference quant_block.py:98-119); x2 = skip tensor to concat."""
     dev = x.t.device
-    te = linear(blk.time_emb_proj, ops.row_quant(silu_emb, [blk.time_emb_proj.act_qparam(dev)])[0])
+    te = linear(blk.time_emb_proj, *quant_rows(silu_emb, blk.time_emb_proj))
     h = conv(blk.conv1, x, x2=x2, gn=_gn(blk.norm1, x, x2), act=1, temb=te)
     if blk.conv_shortcut is not None:
         sc = conv(blk.conv_shortcut, x, x2=x2).t
@@ -210,15 +229,14 @@ def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: i
     return out
 
 
-def attention(attn, xq: torch.Tensor, xk: torch.Tensor, xv: torch.Tensor, b: int, t: int, s: int,
-              resid: Optional[torch.Tensor]) -> torch.Tensor:
-    """Attention_forward given the three already-quantised projection inputs."""
-    dev = xq.device
-    q = linear(attn.to_q, xq)
-    k = linear(attn.to_k, xk)
-    v = linear(attn.to_v, xv)
+def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torch.Tensor]) -> torch.Tensor:
+    """Attention_forward given the three already-quantised projection inputs (operands xq/xk/xv
+    written under quantizers qs = [q_to_q, q_to_k, q_to_v])."""
+    q = linear(attn.to_q, xq, qs[0])
+    k = linear(attn.to_k, xk, qs[1])
+    v = linear(attn.to_v, xv, qs[2])
     o = attention_core(attn, q, k, v, b, t, s)
-    return linear(attn.to_out[0], ops.row_quant(o, [attn.to_out[0].act_qparam(dev)])[0], resid=resid)
+    return linear(attn.to_out[0], *quant_rows(o, attn.to_out[0]), resid=resid)
 
 
 def _ctx_operand(ctx: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
@@ -234,23 +252,26 @@ def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor]) -> Act:
     dev = h.t.device
     b, t = h.b, h.rows
     a1, a2, ff = blk.attn1, blk.attn2, blk.ff
-    xs = ops.ln_quant(h.t, _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps,
-                      [a1.to_q.act_qparam(dev), a1.to_k.act_qparam(dev), a1.to_v.act_qparam(dev)])
-    x = attention(a1, xs[0], xs[1], xs[2], b, t, t, resid=h.t)
+    qs = [a1.to_q.act_qparam(dev), a1.to_k.act_qparam(dev), a1.to_v.act_qparam(dev)]
+    xs = ops.ln_quant(h.t, _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps, qs, emit_int=EXACT_INT)
+    x = attention(a1, xs[0], xs[1], xs[2], qs, b, t, t, resid=h.t)
     if ctx is not None:
         cx, cb, s = _ctx_operand(ctx)
-        xq = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps,
-                          [a2.to_q.act_qparam(dev)])[0]
-        xkv = ops.row_quant(cx, [a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)])
-        x = attention(a2, xq, xkv[0], xkv[1], b, t, s, resid=x)
+        qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
+        xq = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs[:1],
+                          emit_int=EXACT_INT)[0]
+        xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
+        x = attention(a2, xq, xkv[0], xkv[1], qs, b, t, s, resid=x)
     else:
-        xs = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps,
-                          [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)])
-        x = attention(a2, xs[0], xs[1], xs[2], b, t, t, resid=x)
+        qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
+        xs = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs, emit_int=EXACT_INT)
+        x = attention(a2, xs[0], xs[1], xs[2], qs, b, t, t, resid=x)
     proj, out = ff.net[0].proj, ff.net[2]
-    x3 = ops.ln_quant(x, _f32(blk.norm3.weight), _f32(blk.norm3.bias), blk.norm3.eps, [proj.act_qparam(dev)])[0]
-    g = linear(proj, x3)
-    x = linear(out, ops.geglu_quant(g, out.act_qparam(dev)), resid=x)
+    qp = proj.act_qparam(dev)
+    x3 = ops.ln_quant(x, _f32(blk.norm3.weight), _f32(blk.norm3.bias), blk.norm3.eps, [qp], emit_int=EXACT_INT)[0]
+    g = linear(proj, x3, qp)
+    qo = out.act_qparam(dev)
+    x = linear(out, ops.geglu_quant(g, qo, emit_int=EXACT_INT), qo, resid=x)
     return Act(x, h.b, h.h, h.w)
 
 
@@ -258,14 +279,18 @@ def transformer2d(mod, x: Act, ctx: Optional[torch.Tensor]) -> Act:
     """Transformer2DModel.forward (sd.py:283-305 conv proj; sdxl.py:306-326 linear proj): in NHWC
     both are the same GEMM, and the NCHW<->token permutes of the reference disappear."""
     dev = x.t.device
-    h = conv(mod.proj_in, x, gn=_gn(mod.norm, x)) if mod.proj_in.is_conv else Act(
-        linear(mod.proj_in, ops.act_producer(x.t, batch=x.b, h=x.h, w=x.w, ksize=1, gn=_gn(mod.norm, x),
-                                             q=mod.proj_in.act_qparam(dev))), x.b, x.h, x.w)
+    if mod.proj_in.is_conv:
+        h = conv(mod.proj_in, x, gn=_gn(mod.norm, x))
+    else:
+        qi = mod.proj_in.act_qparam(dev)
+        a_op = ops.act_producer(x.t, batch=x.b, h=x.h, w=x.w, ksize=1, gn=_gn(mod.norm, x), q=qi,
+                                emit_int=_exact(qi))
+        h = Act(linear(mod.proj_in, a_op, qi), x.b, x.h, x.w)
     for blk in mod.transformer_blocks:
         h = transformer_block(blk, h, ctx)
     if mod.proj_out.is_conv:
         return conv(mod.proj_out, h, resid=x.t)
-    y = linear(mod.proj_out, ops.row_quant(h.t, [mod.proj_out.act_qparam(dev)])[0], resid=x.t)
+    y = linear(mod.proj_out, *quant_rows(h.t, mod.proj_out), resid=x.t)
     return Act(y, x.b, x.h, x.w)
 
 

@@ -56,9 +56,16 @@ class QParam:
     zp: Optional[torch.Tensor] = None
     period: int = 1
     qmax: float = 255.0
+    int_ok: bool = False   # |code - zp| <= 2048 for every entry: the integer operand is exact in fp16
 
-    def struct(self) -> L.QuantT:
-        return L.QuantT(_p(self.delta), _p(self.zp), self.mode, self.period, self.qmax)
+    def struct(self, emit_int: bool = False) -> L.QuantT:
+        return L.QuantT(_p(self.delta), _p(self.zp), self.mode, self.period, self.qmax, int(emit_int))
+
+    @property
+    def exact(self) -> bool:
+        """scalar / row-wise scales can leave the GEMM exact: integer A, delta applied per row in the
+        epilogue.  K-wise scales vary along the reduction and must be folded into the fp16 operand."""
+        return self.int_ok and self.mode in (Q_SCALAR, Q_ROWWISE)
 
 
 NOQ = QParam()
@@ -71,8 +78,9 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     `conv`: the quantizer saw the unfolded (B, C*kh*kw, L) tensor, so the axes swap.  `kperm`
     re-orders a K-wise table into the GEMM's K order (conv: tap-major)."""
     d, z = _f32(delta, device), _f32(zp, device)
+    int_ok = bool((z.abs().max() + qmax <= 2048).item())
     if d.dim() == 0 or d.numel() == 1 and d.dim() <= 1:
-        return QParam(Q_SCALAR, d.reshape(1), z.reshape(1).expand(1).contiguous(), 1, qmax)
+        return QParam(Q_SCALAR, d.reshape(1), z.reshape(1).expand(1).contiguous(), 1, qmax, int_ok)
     if d.dim() == 3 and d.shape[0] == 1 and d.shape[1] == 1:      # (1,1,X): last axis
         mode = Q_ROWWISE if conv else Q_KWISE
     elif d.dim() == 3 and d.shape[0] == 1 and d.shape[2] == 1:    # (1,X,1): middle axis
@@ -82,7 +90,7 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     d, z = d.reshape(-1), z.reshape(-1).expand(d.numel())
     if kperm is not None and mode == Q_KWISE:
         d, z = d[kperm], z[kperm]
-    return QParam(mode, d.contiguous(), z.contiguous(), d.numel(), qmax)
+    return QParam(mode, d.contiguous(), z.contiguous(), d.numel(), qmax, int_ok)
 
 
 # ------------------------------------------------------------------------------------------
@@ -145,7 +153,7 @@ def pack_weight(w: torch.Tensor, delta, zp, alpha, qmax: float, use_wq: bool, *,
 def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Optional[torch.Tensor] = None,
                  upsample: bool = False, ksize: int = 1, stride: int = 1, gn=None, act: int = 0,
                  q: QParam = NOQ, pad_quantized: bool = False, ldo: Optional[int] = None,
-                 want_codes: bool = False):
+                 want_codes: bool = False, emit_int: bool = False):
     """src NHWC ([batch, hs, ws, c], fp16 or fp32) -> fp16 A operand [M, ldo] (+ codes).
     gn = (mean, rstd, gamma, beta) or None."""
     c0 = src0.shape[-1]
@@ -161,7 +169,7 @@ def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Option
     a = L.ProducerT(_p(src0), _p(src1), c0, c1, int(src0.dtype == torch.float32), batch, h, w, int(upsample),
                     ksize, stride, pad,
                     _p(gn[0]) if gn else None, _p(gn[1]) if gn else None, _p(gn[2]) if gn else None,
-                    _p(gn[3]) if gn else None, act, q.struct(), int(pad_quantized), _p(out), ldo, _p(codes))
+                    _p(gn[3]) if gn else None, act, q.struct(emit_int), int(pad_quantized), _p(out), ldo, _p(codes))
     L.check(L.lib().dgq_act_producer(C.byref(a), _stream()), "dgq_act_producer")
     _count()
     return (out, codes) if want_codes else out
@@ -180,25 +188,26 @@ def gn_stats(src0: torch.Tensor, src1: Optional[torch.Tensor], batch: int, hw: i
     return mean, rstd
 
 
-def _row_outputs(x, qs):
+def _row_outputs(x, qs, emit_int=False):
     m, c = x.shape
     outs = [torch.empty(m, c, dtype=torch.float16, device=x.device) for _ in qs]
-    qarr = (L.QuantT * len(qs))(*[q.struct() for q in qs])
+    qarr = (L.QuantT * len(qs))(*[q.struct(emit_int and q.exact) for q in qs])
     oarr = (C.c_void_p * len(qs))(*[o.data_ptr() for o in outs])
     return outs, qarr, oarr
 
 
-def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, qs: Sequence[QParam]):
-    """x fp16 [m, c] -> [fp16 [m, c]] * len(qs)."""
-    outs, qarr, oarr = _row_outputs(x, qs)
+def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, qs: Sequence[QParam],
+             emit_int: bool = False):
+    """x [m, c] -> [fp16 [m, c]] * len(qs); emit_int: integer operands for the quantizers that allow it."""
+    outs, qarr, oarr = _row_outputs(x, qs, emit_int)
     L.check(L.lib().dgq_ln_quant(_p(x), _is32(x), x.shape[0], x.shape[1], _p(gamma), _p(beta), eps, len(qs), qarr,
                                  oarr, _stream()), "dgq_ln_quant")
     _count()
     return outs
 
 
-def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False):
-    outs, qarr, oarr = _row_outputs(x, qs)
+def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False, emit_int: bool = False):
+    outs, qarr, oarr = _row_outputs(x, qs, emit_int)
     codes = [torch.empty(x.shape, dtype=torch.uint8, device=x.device) for _ in qs] if want_codes else None
     carr = (C.c_void_p * len(qs))(*[c.data_ptr() for c in codes]) if want_codes else None
     L.check(L.lib().dgq_row_quant(_p(x), int(x.dtype == torch.float32), x.shape[0], x.shape[1], len(qs), qarr,
@@ -207,16 +216,18 @@ def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False):
     return (outs, codes) if want_codes else outs
 
 
-def geglu_quant(x: torch.Tensor, q: QParam) -> torch.Tensor:
+def geglu_quant(x: torch.Tensor, q: QParam, emit_int: bool = False) -> torch.Tensor:
     m, f2 = x.shape
     out = torch.empty(m, f2 // 2, dtype=torch.float16, device=x.device)
-    L.check(L.lib().dgq_geglu_quant(_p(x), _is32(x), m, f2 // 2, q.struct(), _p(out), _stream()), "dgq_geglu_quant")
+    L.check(L.lib().dgq_geglu_quant(_p(x), _is32(x), m, f2 // 2, q.struct(emit_int and q.exact), _p(out), _stream()),
+            "dgq_geglu_quant")
     _count()
     return out
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, temb=None, rows_per_batch: int = 0,
-         resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None):
+         resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None,
+         row_scale: Optional[torch.Tensor] = None, row_period: int = 1):
     """a fp16 [m, lda], b fp16 [n_pad, ldb] -> [m, n] (n multiple of 8), fp32 if want_f32 (or `out`
     is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32)."""
     m = a.shape[0]
@@ -230,7 +241,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
             ep32 = _is32(e)
     if temb is not None and resid is not None and _is32(temb) != _is32(resid):
         raise TypeError("temb and resid must have the same dtype")
-    g = L.GemmT(_p(a), a.stride(0), _p(b), b.stride(0), m, n, k, _p(scale), _p(bias), _p(temb), rows_per_batch,
+    g = L.GemmT(_p(a), a.stride(0), _p(b), b.stride(0), m, n, k, _p(scale), _p(row_scale), row_period, _p(bias),
+                _p(temb), rows_per_batch,
                 temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
                 None if o32 else _p(out), out.stride(0), _p(out) if o32 else None, ep32)
     L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")

@@ -70,9 +70,10 @@ def load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor] = None, use_
                 m.delta, m.zero_point = nn.Parameter(m.delta.detach()), nn.Parameter(m.zero_point.detach())
     for key in [k for k in ckpt if "aqtizer" in k]:
         del ckpt[key]
-    target = qnn if "model" in next(iter(ckpt)) else qnn.model
-    missing = target.load_state_dict(ckpt, strict=False)
-    logger.info(f"keys not loaded: {missing}")
+    if ckpt:
+        target = qnn if "model" in next(iter(ckpt)) else qnn.model
+        missing = target.load_state_dict(ckpt, strict=False)
+        logger.info(f"keys not loaded: {missing}")
     qnn.set_quant_state(use_wq=True, use_aq=False)
 
     if use_aq:

@@ -47,6 +47,7 @@ class QuantModel(nn.Module):
         self._step_tables: Optional[List[Dict[str, object]]] = None
         self._num_inference_steps = None
         self._graphs = {}
+        self._use_graphs = False
 
     # -- tree surgery (reference :66-103) ---------------------------------------------------
     def quant_module(self, module, wq_params={}, aq_params={}, aq_mode=[QMODE.NORMAL.value], prev_name=None):
@@ -117,6 +118,8 @@ class QuantModel(nn.Module):
         self._step_tables = flips
         self._num_inference_steps = num_inference_steps
         self._named = named
+        self._tabled = [named[p] for p in qtables]
+        self._cur_step = -1
         self._graphs.clear()
 
     def step_index(self, timesteps: torch.Tensor) -> int:
@@ -129,18 +132,69 @@ class QuantModel(nn.Module):
             return
         if not 0 <= idx < len(self._step_tables):
             raise KeyError(f"act_{idx}")  # the reference raises KeyError on a missing act_k
+        if idx == self._cur_step:
+            return
         for k in range(idx + 1):          # sticky flags accumulate in step order
             for owner_path in self._step_tables[k]:
                 self._named[owner_path].use_group_num = True
-        for m in self.modules():
-            if isinstance(m, UniformAffineQuantizer) and m._table is not None:
-                m._step = idx
+        for m in self._tabled:
+            m._step = idx
+        self._cur_step = idx
 
     # -- forward ------------------------------------------------------------------------------
     def forward(self, sample, timesteps, encoder_hidden_states, *args, **kwargs):
+        idx = 0
         if self._step_tables is not None:
-            self.set_step(self.step_index(timesteps))
+            idx = self.step_index(timesteps)
+            self.set_step(idx)
+        if self._use_graphs and sample.is_cuda:
+            return self._graph_forward(idx, sample, timesteps, encoder_hidden_states, *args, **kwargs)
         return self.model(sample, timesteps, encoder_hidden_states, *args, **kwargs)
+
+    # -- CUDA graphs: one per (step index, input shapes) --------------------------------------
+    def enable_cuda_graphs(self, on: bool = True) -> None:
+        """Replay a captured graph per (step, shape) instead of ~3.5k python-dispatched launches.
+        Quantizer state must not change afterwards (set_quant_state / set_step_tables clear it)."""
+        self._use_graphs = on
+        if not on:
+            self._graphs.clear()
+
+    def _graph_forward(self, idx, sample, timesteps, ctx, *args, **kwargs):
+        added = kwargs.get("added_cond_kwargs", args[0] if args else None)
+        key = (idx, tuple(sample.shape), sample.dtype, tuple(ctx.shape), ctx.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = {"sample": sample.clone(), "t": timesteps.clone().to(sample.device), "ctx": ctx.clone(),
+                  "added": None if added is None else {k: v.clone().to(sample.device) for k, v in added.items()}}
+
+            def call():
+                if st["added"] is not None:
+                    return self.model(st["sample"], st["t"], st["ctx"], st["added"])
+                return self.model(st["sample"], st["t"], st["ctx"])
+            from .. import ops
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):     # warm-up: lazy weight packing, allocator pools
+                call()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            n0 = ops.LAUNCHES
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = call()
+            ent = {"graph": graph, "st": st, "out": out, "launches": ops.LAUNCHES - n0}
+            self._graphs[key] = ent
+        st = ent["st"]
+        st["sample"].copy_(sample, non_blocking=True)
+        st["t"].copy_(timesteps.to(st["t"].dtype), non_blocking=True)
+        st["ctx"].copy_(ctx, non_blocking=True)
+        if st["added"] is not None:
+            for k, v in added.items():
+                st["added"][k].copy_(v, non_blocking=True)
+        ent["graph"].replay()
+        from .. import ops
+        ops.LAUNCHES += ent["launches"]
+        return [ent["out"][0]]
 
     def half(self):
         return self  # compute is fp16 already; parameters and scales stay fp32 (quantisation is done in fp32)

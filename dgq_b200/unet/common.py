@@ -91,15 +91,15 @@ class Attention(nn.Module):
         b, t, c = hidden_states.shape
         x = hidden_states.detach().reshape(b * t, c)
         x = x.contiguous() if x.dtype in (torch.float32, torch.float16) else x.float().contiguous()
+        qs = [self.to_q.act_qparam(dev), self.to_k.act_qparam(dev), self.to_v.act_qparam(dev)]
         if encoder_hidden_states is not None:
             cx, _, s = engine._ctx_operand(encoder_hidden_states)
-            xq = ops.row_quant(x, [self.to_q.act_qparam(dev)])[0]
-            xk, xv = ops.row_quant(cx, [self.to_k.act_qparam(dev), self.to_v.act_qparam(dev)])
+            xq = ops.row_quant(x, qs[:1], emit_int=engine.EXACT_INT)[0]
+            xk, xv = ops.row_quant(cx, qs[1:], emit_int=engine.EXACT_INT)
         else:
             s = t
-            xq, xk, xv = ops.row_quant(x, [self.to_q.act_qparam(dev), self.to_k.act_qparam(dev),
-                                           self.to_v.act_qparam(dev)])
-        out = engine.attention(self, xq, xk, xv, b, t, s, resid=None)
+            xq, xk, xv = ops.row_quant(x, qs, emit_int=engine.EXACT_INT)
+        out = engine.attention(self, xq, xk, xv, qs, b, t, s, resid=None)
         return out.view(b, t, -1).to(hidden_states.dtype)
 
     def forward(self, hidden_states, encoder_hidden_states=None):
@@ -116,7 +116,7 @@ class GEGLU(nn.Module):
         shp = x.shape
         x2 = x.detach().reshape(-1, shp[-1])
         x2 = x2.contiguous() if x2.dtype in (torch.float32, torch.float16) else x2.float().contiguous()
-        g = engine.linear(self.proj, ops.row_quant(x2, [self.proj.act_qparam(x.device)])[0])
+        g = engine.linear(self.proj, *engine.quant_rows(x2, self.proj))
         return ops.geglu_quant(g, ops.NOQ).view(*shp[:-1], -1).to(x.dtype)
 
 

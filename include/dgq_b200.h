@@ -39,9 +39,12 @@ extern "C" {
 typedef struct {
   const float* delta; /* device, 1 or many entries depending on mode */
   const float* zp;
-  int mode;   /* DGQ_Q_*            */
-  int period; /* DGQ_Q_ROWWISE only */
-  float qmax; /* 2^bits - 1         */
+  int mode;     /* DGQ_Q_*            */
+  int period;   /* DGQ_Q_ROWWISE only */
+  float qmax;   /* 2^bits - 1         */
+  int emit_int; /* producers only: write the integer (code - zp), exact in fp16, instead of
+                   delta * (code - zp); the consumer GEMM applies delta per row (row_scale).
+                   Valid for SCALAR / ROWWISE, |code - zp| <= 2048.                          */
 } dgq_quant_t;
 
 int dgq_version(void);
@@ -118,7 +121,7 @@ int dgq_row_quant(const void* x, int src_is_f32, int m, int c, int n_out, const 
  * x: fp16/fp32 [m, 2f] -> out fp16 [m, f]                                                       */
 int dgq_geglu_quant(const void* x, int src_is_f32, int m, int f, dgq_quant_t q, void* out, void* stream);
 
-/* ---- qGEMM: C[m, n] = (A[m, k] . B[n, k]^T) * scale[n] + bias[n] (+ temb[m / rows_per_batch, n])
+/* ---- qGEMM: C[m, n] = (A[m, k] . B[n, k]^T) * row_scale[m] * scale[n] + bias[n] (+ temb[m / rows_per_batch, n])
  *      (+ resid[m, n]) on tcgen05/TMEM, TMA-fed (replaces F.linear / F.conv2d / W.view(Co,-1) @ x_unf,
  *      quant/quant_layer.py:649-659; residual and temb adds quant/quant_block.py:105-117,165-186).
  * A: fp16 [m, lda]; B: fp16 [n_pad, ldb] = (code - zp) from dgq_pack_weight; k multiple of 8;
@@ -128,6 +131,10 @@ typedef struct {
   const void* b; int ldb;
   int m, n, k;
   const float* scale;  /* [n] per-out-channel weight delta, or NULL (=1) */
+  const float* row_scale; /* activation delta applied per row: row_scale[(m % row_period)], or NULL.
+                             With integer A (dgq_quant_t.emit_int) and integer B the accumulation is
+                             exact, so the result matches the fp32 reference to rounding of the sum. */
+  int row_period;      /* 1: scalar delta */
   const float* bias;   /* [n] or NULL */
   const void* temb;    /* [m / rows_per_batch, ld_temb] or NULL; fp32 when ep_is_f32 else fp16 */
   int rows_per_batch, ld_temb;
