@@ -26,7 +26,8 @@
 
 namespace dgq {
 
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;          // warp 0 loader, warp 1 MMA, warps 2..9 softmax
+constexpr int kSoftmaxThreads = 256;
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 x 64] fp16 SW128 sub-tile
@@ -49,19 +50,58 @@ struct AttnDev {
   uint8_t* codes;
 };
 
-struct AttnSmem {
-  uint8_t* q;
-  uint8_t* k;
-  uint8_t* v;
-  uint8_t* p;
-  uint64_t* bars;
-};
-
 // barrier indices
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11,
        B_PFULL = 13, B_PEMPTY = 15, B_OFULL = 17, B_COUNT = 18 };
 
-template <int PASS>
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_bar_sync() {  // the 8 softmax warps only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// ---- pass 2, 32 scores of one row -> 32 fp16 operand values P' (packed in 16 regs)
+//   MODE LOG2   : P' = 2^-code, code = clamp(rint(gamma - s*alpha), 0, qcap)   (no MUFU at all)
+//   MODE UNIFORM: P' = code = min(rint(2^(s*alpha - gamma)), qmax)
+//   MODE NONE   : P' = 2^(s*alpha - gamma)
+template <int MODE, bool MASK, bool CODES>
+__device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2)[16], float alpha, float gamma,
+                                          float qcap, float qmax, int col0, int s_len, uint8_t* code_row) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float pv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float sc = __uint_as_float(r[i + e]);
+      float val;
+      if (MODE == DGQ_MAP_LOG2) {
+        // rint through the 1.5*2^23 magic add; 2^-code rebuilt from the exponent field
+        const float xq = fminf(fmaxf(fmaf(-alpha, sc, gamma), 0.f), qcap);
+        const uint32_t yb = __float_as_uint(xq + 12582912.0f);
+        val = __uint_as_float(yb * 0xFF800000u + 0x3F800000u);
+      } else if (MODE == DGQ_MAP_UNIFORM) {
+        val = fminf(rintf(ex2_approx(fmaf(alpha, sc, -gamma))), qmax);
+      } else {
+        val = ex2_approx(fmaf(alpha, sc, -gamma));
+      }
+      if (MASK) val = (col0 + i + e < s_len) ? val : 0.f;
+      if (CODES) {
+        if (col0 + i + e < s_len && MODE != DGQ_MAP_NONE) {
+          const float cd = MODE == DGQ_MAP_LOG2 ? fminf(rintf(fmaxf(fmaf(-alpha, sc, gamma), 0.f)), qmax) : val;
+          code_row[col0 + i + e] = static_cast<uint8_t>(cd);
+        }
+      }
+      pv[e] = val;
+    }
+    const __half2 hh = __floats2half2_rn(pv[0], pv[1]);
+    h2[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+}
+
+template <int PASS, int MODE, bool CODES>
 __global__ void __launch_bounds__(kAttThreads, PASS == 1 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnDev p) {
@@ -77,7 +117,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* s_end = s_p + (PASS == 2 ? 2 * 2 * kChunkBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_end);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [dp] v_hat row 0 (start-peak)
+  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [192] v_hat row 0 (start-peak)
+  float* s_x = s_v0 + 192;                                 // [3][128] cross-half exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x % p.q_tiles;
@@ -89,8 +130,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     prefetch_tmap(&tm_k);
     if (PASS == 2) prefetch_tmap(&tm_v);
     for (int i = 0; i < B_COUNT; ++i) {
-      const bool four = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2);
-      mbar_init(&bars[i], four ? 4 : 1);
+      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2);
+      mbar_init(&bars[i], all_sm ? 8 : 1);
     }
     fence_barrier_init();
   }
@@ -100,7 +141,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tmem_relinquish();
   }
   if (PASS == 2 && p.start_peak && threadIdx.x >= 64) {
-    for (int dd = threadIdx.x - 64; dd < p.dp; dd += 128)
+    for (int dd = threadIdx.x - 64; dd < p.dp; dd += kSoftmaxThreads)
       s_v0[dd] = __half2float(p.vt[(static_cast<size_t>(bh) * p.dp + dd) * p.sp]);
   }
   tc_fence_before();
@@ -174,8 +215,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps
+    // ------------------------------------------------------------------ softmax warps (2..9)
+    // warp -> TMEM lane quarter (warp & 3) and column half ((warp - 2) >> 2): one thread per
+    // (row, 64-column half) of the 128 x 128 score tile
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;           // row inside the tile == TMEM lane
     const int tq = q_tile * kTileQ + row;       // query index
     const bool row_ok = tq < p.t;
@@ -190,20 +234,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(&bars[B_SFULL + sb], (j >> 1) & 1);
         tc_fence_after();
         const bool mask = partial_last && j == p.nkv - 1;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + c * 32, r);
           tc_wait_ld();
           float x[32];
-          float cm = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            x[i] = __uint_as_float(r[i]) * p.alpha;
-            if (mask && (j * kTileK + c * 32 + i >= p.s)) x[i] = -INFINITY;
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) * p.alpha;
+          if (mask) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = (j * kTileK + c * 32 + i < p.s) ? x[i] : -INFINITY;
           }
+          float cm = x[1];
 #pragma unroll
-          for (int i = 1; i < 32; ++i) cm = fmaxf(cm, x[i]);
+          for (int i = 2; i < 32; ++i) cm = fmaxf(cm, x[i]);
           const float cmx = cm;                 // excludes element 0 of this chunk
           cm = fmaxf(cm, x[0]);
           Mx = fmaxf(Mx, (j == 0 && c == 0) ? cmx : cm);
@@ -211,8 +257,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (Mn > -INFINITY) {
             float acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc += exp2f(x[i] - Mn);
-            l = l * exp2f(M - Mn) + acc;
+            for (int i = 0; i < 32; ++i) acc += ex2_approx(x[i] - Mn);
+            l = l * ex2_approx(M - Mn) + acc;
             M = Mn;
           }
         }
@@ -220,72 +266,57 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
       }
-      float rp = 0.f;
-      if (row_ok) {
-        p.row_max[ridx] = M;
-        p.row_sum[ridx] = l;
-        rp = (p.start_peak ? exp2f(Mx - M) : 1.0f) / l;
+      // combine the two column halves of each row
+      if (half == 1) { s_x[row] = M; s_x[128 + row] = l; s_x[256 + row] = Mx; }
+      softmax_bar_sync();
+      if (half == 0) {
+        const float M1 = s_x[row], l1 = s_x[128 + row], Mx1 = s_x[256 + row];
+        const float Mn = fmaxf(M, M1);
+        if (Mn > -INFINITY) l = l * ex2_approx(M - Mn) + l1 * ex2_approx(M1 - Mn);
+        M = Mn;
+        Mx = fmaxf(Mx, Mx1);
+        float rp = 0.f;
+        if (row_ok) {
+          p.row_max[ridx] = M;
+          p.row_sum[ridx] = l;
+          rp = (p.start_peak ? ex2_approx(Mx - M) : 1.0f) / l;
+        }
+        for (int o = 16; o > 0; o >>= 1) rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, o));
+        if (lane == 0 && p.real_time) atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(rp));
       }
-      for (int o = 16; o > 0; o >>= 1) rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, o));
-      if (lane == 0 && p.real_time) atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(rp));
     } else {
       // ---------------------------------------------------------------- pass 2
       float delta = 1.0f;
-      if (p.map_mode != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
+      if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
       const float beta = row_ok ? (p.row_max[ridx] + log2f(p.row_sum[ridx])) : 0.f;
-      const float gamma = beta + (p.map_mode != DGQ_MAP_NONE ? log2f(delta) : 0.f);
+      const float gamma = beta + (MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f);
       const float qcap = fminf(p.qmax, 126.f);
       float p0 = 0.f;                           // un-quantised start-peak probability of this row
+      uint8_t* code_row = CODES ? p.codes + ridx * p.s : nullptr;
       for (int j = 0; j < p.nkv; ++j) {
         const int sb = j & 1;
         mbar_wait(&bars[B_SFULL + sb], (j >> 1) & 1);
         mbar_wait(&bars[B_PEMPTY + sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const bool mask = partial_last && j == p.nkv - 1;
-        uint8_t* prow = s_p + sb * 2 * kChunkBytes;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        const bool mask = (partial_last && j == p.nkv - 1) || (CODES && !row_ok);
+        uint8_t* sub = s_p + sb * 2 * kChunkBytes + half * kChunkBytes;   // this half's [128 x 64] sub-tile
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = half * 2 + cc;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + c * 32, r);
           tc_wait_ld();
           uint32_t h2[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float pv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float sa = __uint_as_float(r[i + e]) * p.alpha;
-              float val;
-              if (p.map_mode == DGQ_MAP_LOG2) {
-                // rint through the 1.5*2^23 magic add; 2^-code rebuilt from the exponent field
-                float xq = fminf(fmaxf(gamma - sa, 0.f), qcap);
-                const uint32_t yb = __float_as_uint(xq + 12582912.0f);
-                val = __uint_as_float(yb * 0xFF800000u + 0x3F800000u);
-              } else if (p.map_mode == DGQ_MAP_UNIFORM) {
-                val = fminf(rintf(exp2f(sa - gamma)), p.qmax);
-              } else {
-                val = exp2f(sa - gamma);
-              }
-              const int col = j * kTileK + c * 32 + i + e;
-              if (mask && col >= p.s) val = 0.f;
-              if (p.codes != nullptr && row_ok && col < p.s && p.map_mode != DGQ_MAP_NONE) {
-                const float cd = p.map_mode == DGQ_MAP_LOG2 ? fminf(rintf(fmaxf(gamma - sa, 0.f)), p.qmax) : val;
-                p.codes[ridx * p.s + col] = static_cast<uint8_t>(cd);
-              }
-              pv[e] = val;
-            }
-            if (p.start_peak && j == 0 && c == 0 && i == 0) {
-              p0 = exp2f(__uint_as_float(r[0]) * p.alpha - beta);
-              pv[0] = 0.f;
-            }
-            const __half2 hh = __floats2half2_rn(pv[0], pv[1]);
-            h2[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          const int col0 = j * kTileK + c * 32;
+          if (mask) map_chunk<MODE, true, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, col0, row_ok ? p.s : 0, code_row);
+          else map_chunk<MODE, false, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, col0, p.s, code_row);
+          if (p.start_peak && j == 0 && c == 0) {
+            p0 = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0]), -beta));
+            h2[0] &= 0xFFFF0000u;               // column 0 leaves the MMA; added back in the epilogue
           }
-          // 32 halves = 4 x 16 B chunks of this row; key chunk (c>>1), 16B-chunk (c&1)*4 + v
-          uint8_t* sub = prow + (c >> 1) * kChunkBytes;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            *reinterpret_cast<uint4*>(sub + sw128_offset(row, (c & 1) * 4 + v)) =
+            *reinterpret_cast<uint4*>(sub + sw128_offset(row, cc * 4 + v)) =
                 make_uint4(h2[4 * v], h2[4 * v + 1], h2[4 * v + 2], h2[4 * v + 3]);
           }
         }
@@ -297,15 +328,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           mbar_arrive(&bars[B_PFULL + sb]);
         }
       }
-      // ---- epilogue: O * out_scale (+ p0 * v0) -> fp16
+      // ---- epilogue: O * out_scale (+ p0 * v0) -> out; the two halves split the dp columns
+      if (p.start_peak) {
+        if (half == 0) s_x[row] = p0;
+        softmax_bar_sync();
+        p0 = s_x[row];
+      }
       mbar_wait(&bars[B_OFULL], 0);
       tc_fence_after();
-      const float oscale = p.map_mode == DGQ_MAP_NONE ? 1.0f : delta;
+      const float oscale = MODE == DGQ_MAP_NONE ? 1.0f : delta;
       const int head = bh % p.heads, bb = bh / p.heads;
       const size_t ooff = (static_cast<size_t>(bb) * p.t + tq) * p.ldo + head * p.d;
       __half* orow = static_cast<__half*>(p.out) + ooff;
       float* orow32 = static_cast<float*>(p.out) + ooff;
-      for (int c = 0; c < p.dp; c += 32) {
+      const int dhalf = p.dp >> 1;
+      for (int c = half * dhalf; c < (half + 1) * dhalf; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_o + lane_addr + c, r);
         tc_wait_ld();
@@ -318,7 +355,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
-                if (p.start_peak) f[i] += p0 * s_v0[d0 + i];
+                if (p.start_peak) f[i] = fmaf(p0, s_v0[d0 + i], f[i]);
               }
               if (p.out_is_f32) {
                 *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
@@ -375,7 +412,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   AttnDev p;
   p.b = a->b; p.heads = a->heads; p.t = a->t; p.s = a->s; p.d = a->d; p.dp = a->dp;
   p.nkv = (a->s + kTileK - 1) / kTileK;
-  p.kv_stages = a->dp <= 128 ? 2 : 1;
+  p.kv_stages = a->dp <= 64 ? 2 : 1;   // smem: dp 128/192 leave room for one K/V stage only
   p.q_tiles = (a->t + kTileQ - 1) / kTileQ;
   p.alpha = a->scale * 1.4426950408889634f;
   p.map_mode = a->map_mode; p.real_time = a->real_time; p.start_peak = a->start_peak;
@@ -394,27 +431,38 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   if (rc != 0) return rc;
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
-  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 192 * 4 + 64;
+  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 192 * 4 + 3 * 128 * 4 + 64;
   const uint32_t smem1 = q_bytes * (1 + p.kv_stages) + tail;
   const uint32_t smem2 = q_bytes * (1 + p.kv_stages) + p.kv_stages * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
-  static uint32_t set1 = 0, set2 = 0;
-  if (smem1 > set1) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    set1 = smem1;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
+  KernelFn k1 = attention_kernel<1, 0, false>;
+  KernelFn k2;
+  const bool cd = a->codes != nullptr;
+  switch (a->map_mode) {
+    case DGQ_MAP_LOG2: k2 = cd ? attention_kernel<2, DGQ_MAP_LOG2, true> : attention_kernel<2, DGQ_MAP_LOG2, false>; break;
+    case DGQ_MAP_UNIFORM: k2 = cd ? attention_kernel<2, DGQ_MAP_UNIFORM, true> : attention_kernel<2, DGQ_MAP_UNIFORM, false>; break;
+    default: k2 = attention_kernel<2, DGQ_MAP_NONE, false>; break;
   }
-  if (smem2 > set2) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    set2 = smem2;
+  // every instantiation gets the maximum it can ever need once (227 KB opt-in)
+  static bool attr_done = false;
+  if (!attr_done) {
+    KernelFn all[] = {attention_kernel<1, 0, false>, attention_kernel<2, DGQ_MAP_LOG2, true>,
+                      attention_kernel<2, DGQ_MAP_LOG2, false>, attention_kernel<2, DGQ_MAP_UNIFORM, true>,
+                      attention_kernel<2, DGQ_MAP_UNIFORM, false>, attention_kernel<2, DGQ_MAP_NONE, false>};
+    for (KernelFn f : all) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    attr_done = true;
   }
+  if (smem2 > 232448) return DGQ_ERR_INVALID_VALUE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = static_cast<int>(bh) * p.q_tiles;
   if (a->real_time) {
     cudaError_t e = cudaMemsetAsync(a->gmax, 0, sizeof(float), s);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  attention_kernel<1><<<grid, kAttThreads, smem1, s>>>(tq, tk, tv, p);
-  attention_kernel<2><<<grid, kAttThreads, smem2, s>>>(tq, tk, tv, p);
+  k1<<<grid, kAttThreads, smem1, s>>>(tq, tk, tv, p);
+  k2<<<grid, kAttThreads, smem2, s>>>(tq, tk, tv, p);
   DGQ_RETURN_LAST_ERROR();
 }
