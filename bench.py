@@ -122,6 +122,18 @@ def run_cuda(args):
             dist.all_gather(gather, y)
         return y.to("cpu", non_blocking=True)
 
+    if args.profile_step:
+        # one eager (no graph) step between cudaProfilerStart/Stop: `ncu --profile-from-start off`
+        # then lists exactly the launches of one step
+        qnn.enable_cuda_graphs(False)
+        with torch.no_grad():
+            call(devin)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
+            call(devin)
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
+        return
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step_resident()
@@ -360,6 +372,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dgq_b200", choices=["dgq_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run one eager step inside cudaProfilerStart/Stop and exit (for ncu)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -16,19 +16,29 @@
 // Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are visited n-fastest so concurrently resident CTAs share A and B
 // tiles through L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace dgq {
 
-constexpr int kBM = 128;
+constexpr int kBM = 128;           // rows of A per CTA
 constexpr int kBK = 64;
 constexpr int kMaxBN = 256;
-constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
-constexpr uint32_t kABytes = kBM * kBK * 2;      // 16 KB
-constexpr uint32_t kBBytes = kMaxBN * kBK * 2;   // 32 KB
-constexpr uint32_t kGemmSmem = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
+constexpr int kStgLd = 36;                         // padded row stride (floats) of the epilogue transpose buffer
+
+template <int kCtas> struct GemmCfg {
+  static constexpr int kStages = kCtas == 1 ? 3 : 5;
+  static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  // [2 buffers][scale | bias][256] fp32 + one [32 rows][36] fp32 transpose buffer per epilogue warp
+  static constexpr uint32_t kEpiBytes = 2 * 2 * kMaxBN * 4 + kEpiWarps * 32 * kStgLd * 4;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct GemmDev {
   int m, n, k, bn;
@@ -47,23 +57,39 @@ struct GemmDev {
   int ep_is_f32;
 };
 
+__device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
+// kCtas == 1: one CTA per 128 x bn tile.  kCtas == 2: a CTA pair (cluster of 2, cta_group::2) per
+// 256 x bn tile -- each CTA stages its own 128 rows of A and bn/2 rows of B, the leader issues the
+// MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
+// L2->smem bytes of the single-CTA tile.
+template <int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
+  using Cfg = GemmCfg<kCtas>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
+  float* s_epi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (leader's copy is the one used)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const int worker = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int workers = static_cast<int>(gridDim.x) / kCtas;
   const int k_blocks = (p.k + kBK - 1) / kBK;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int b_rows = p.bn / kCtas;             // rows of B staged by this CTA
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -74,41 +100,49 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kEpiWarps * kCtas);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (kCtas == 2) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (both CTAs of a pair)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t tx = kABytes + static_cast<uint32_t>(p.bn) * kBK * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t tx = (kABytes + static_cast<uint32_t>(b_rows) * kBK * 2) * kCtas;
+      for (int tile = worker; tile < total_tiles; tile += workers) {
         const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+        const int row_a = m_blk * (kBM * kCtas) + static_cast<int>(rank) * kBM;
+        const int row_b = n_blk * p.bn + static_cast<int>(rank) * b_rows;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], tx);
-          tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(smem_b + stage * kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * p.bn);
+          if (kCtas == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, row_a);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, row_b);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+            tma_load_2d_pair(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, row_a);
+            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, row_b);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM, p.bn);
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBM * kCtas, p.bn);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMaxBN;
@@ -116,98 +150,153 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kABytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * kBBytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int ks = 0; ks < kBK / 16; ++ks) {
             // advancing 16 halves (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            tc_mma_f16(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+            if (kCtas == 2) tc_mma_f16_pair(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+            else tc_mma_f16(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          // frees the smem stage (in both CTAs) once these MMAs retire
+          if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);      // accumulator complete
+        if (kCtas == 2) tc_commit_pair(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quarter this warp may read
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // warp -> TMEM lane quarter (warp & 3) and column half.  Per 32-column chunk: tcgen05.ld (thread
+    // = row) -> row_scale * scale[n] + bias[n] -> per-warp smem transpose -> lanes across columns:
+    // + residual, 128-byte coalesced row-segment stores.  scale / bias (+ the time-embedding row when
+    // the tile lies inside one sample) are staged in smem once per tile; residual segments are
+    // prefetched one chunk ahead.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const int nch = p.bn >> 5;
+    const int c_begin = half == 0 ? 0 : (nch + 1) / 2;
+    const int c_end = half == 0 ? (nch + 1) / 2 : nch;
+    const size_t esz = p.ep_is_f32 ? 4 : 2;
+    const bool temb_tile = p.temb != nullptr && (p.rows_per_batch % (kBM * kCtas)) == 0;
+    float* stg = s_epi + 2 * 2 * kMaxBN + (warp - 2) * (32 * kStgLd);
+    const int rl0 = lane >> 3;          // row (0..3) inside a group of 4 rows
+    const int cq = (lane & 7) * 4;      // first of this lane's 4 columns inside the chunk
+    uint32_t acc = 0, acc_phase = 0, it = 0;
+    for (int tile = worker; tile < total_tiles; tile += workers, ++it) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * kBM + quad * 32 + lane;
+      const int tile_row0 = m_blk * (kBM * kCtas) + static_cast<int>(rank) * kBM;
+      const int warp_row0 = tile_row0 + quad * 32;
+      const int row = warp_row0 + lane;
       const bool row_ok = row < p.m;
-      const size_t esz = p.ep_is_f32 ? 4 : 2;
-      const char* temb_row = (p.temb != nullptr && row_ok)
+      const int ncol0 = n_blk * p.bn;
+      float* s_scale = s_epi + (it & 1) * 2 * kMaxBN;
+      float* s_bias = s_scale + kMaxBN;
+      for (int j = etid; j < p.bn; j += 32 * kEpiWarps) {
+        const int n = ncol0 + j;
+        float sc = 1.0f, bi = 0.0f;
+        if (n < p.n) {
+          if (p.scale != nullptr) sc = __ldg(p.scale + n);
+          if (p.bias != nullptr) bi = __ldg(p.bias + n);
+          if (temb_tile && tile_row0 < p.m) {
+            const size_t off = static_cast<size_t>(tile_row0 / p.rows_per_batch) * p.ld_temb + n;
+            bi += p.ep_is_f32 ? __ldg(static_cast<const float*>(p.temb) + off)
+                              : __half2float(static_cast<const __half*>(p.temb)[off]);
+          }
+        }
+        s_scale[j] = sc;
+        s_bias[j] = bi;
+      }
+      const char* temb_row = (p.temb != nullptr && !temb_tile && row_ok)
                                  ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
                                  : nullptr;
-      const char* resid_row = (p.resid != nullptr && row_ok)
-                                  ? static_cast<const char*>(p.resid) + static_cast<size_t>(row) * p.ld_resid * esz
-                                  : nullptr;
       const float rs = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
-      const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int c = 0; c < p.bn; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c, r);
-        tc_wait_ld();
-        const int n0 = n_blk * p.bn + c;
-        if (row_ok) {
+      float4 t_cur[8], t_nxt[8];
+      auto load_resid = [&](int c, float4 (&t)[8]) {
+        const int n = ncol0 + c * 32 + cq;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int n = n0 + v * 8;
-            if (n < p.n) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]) * rs;
-              if (p.scale != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n + 4));
-                f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
-                f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
-              }
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (temb_row != nullptr) {
-                float t[8];
-                if (p.ep_is_f32) load8(reinterpret_cast<const float*>(temb_row) + n, t);
-                else load8(reinterpret_cast<const __half*>(temb_row) + n, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += t[i];
-              }
-              if (resid_row != nullptr) {
-                float t[8];
-                if (p.ep_is_f32) load8(reinterpret_cast<const float*>(resid_row) + n, t);
-                else load8(reinterpret_cast<const __half*>(resid_row) + n, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] += t[i];
-              }
-              if (p.out != nullptr)
-                *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldc + n) = pack8(f);
-              if (p.out_f32 != nullptr) {
-                float* o = p.out_f32 + static_cast<size_t>(row) * p.ldc + n;
-                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              }
+        for (int rr = 0; rr < 8; ++rr) {
+          const int grow = warp_row0 + rr * 4 + rl0;
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < p.m && n < p.n) {
+            if (p.ep_is_f32) {
+              u = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+            } else {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+              u = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
           }
+          t[rr] = u;
+        }
+      };
+      if (p.resid != nullptr && c_begin < c_end) load_resid(c_begin, t_cur);
+      epi_bar_sync();                       // staged scale / bias visible
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        if (p.resid != nullptr && c + 1 < c_end) load_resid(c + 1, t_nxt);
+        tc_wait_ld();
+        const int j0 = c * 32;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          float f[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            f[i] = fmaf(__uint_as_float(r[v * 4 + i]) * rs, s_scale[j0 + v * 4 + i], s_bias[j0 + v * 4 + i]);
+          if (temb_row != nullptr && ncol0 + j0 + v * 4 < p.n) {
+            const int n = ncol0 + j0 + v * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              f[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n + i]
+                                  : __half2float(reinterpret_cast<const __half*>(temb_row)[n + i]);
+          }
+          *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(f[0], f[1], f[2], f[3]);
+        }
+        __syncwarp();
+        const int n = ncol0 + j0 + cq;
+        if (n < p.n) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int rl = rr * 4 + rl0;
+            const int grow = warp_row0 + rl;
+            if (grow < p.m) {
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+              if (p.resid != nullptr) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+              const size_t o = static_cast<size_t>(grow) * p.ldc + n;
+              if (p.out != nullptr) {
+                const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              }
+              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+            }
+          }
+        }
+        __syncwarp();
+        if (p.resid != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -268,16 +357,26 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   DGQ_CHECK_ARG(a->resid == nullptr || a->ld_resid % 8 == 0);
 
   static bool attr_set = false;
+  static int force_ctas = 0;   // DGQ_GEMM_CTAS=1|2 pins the variant (benchmarking); default: by problem size
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<1>::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaFuncSetAttribute(gemm_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const char* env = getenv("DGQ_GEMM_CTAS");
+    if (env != nullptr) force_ctas = atoi(env);
     attr_set = true;
   }
   GemmDev p;
   p.m = a->m; p.n = a->n; p.k = a->k;
   p.bn = pick_bn(a->n);
-  p.m_tiles = (a->m + kBM - 1) / kBM;
   p.n_tiles = (a->n + p.bn - 1) / p.bn;
+  // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; small problems keep
+  // 128-row tiles on single CTAs so more SMs get a tile
+  int ctas = (a->m > kBM && ((a->m + 2 * kBM - 1) / (2 * kBM)) * p.n_tiles >= kNumSMs / 2) ? 2 : 1;
+  if (force_ctas == 1 || force_ctas == 2) ctas = force_ctas;
+  p.m_tiles = (a->m + kBM * ctas - 1) / (kBM * ctas);
   p.scale = a->scale; p.bias = a->bias;
   p.row_scale = a->row_scale; p.row_period = a->row_period > 0 ? a->row_period : 1;
   p.temb = a->temb;
@@ -290,11 +389,30 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM);
   if (rc != 0) return rc;
   // B rows beyond n are zero-filled by TMA (out-of-bounds box rows)
-  rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn);
+  rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn / ctas);
   if (rc != 0) return rc;
 
   const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_f16_kernel<<<grid, kGemmThreads, kGemmSmem, static_cast<cudaStream_t>(stream)>>>(ta, tb, p);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ctas == 1) {
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    gemm_f16_kernel<1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, s>>>(ta, tb, p);
+  } else {
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = GemmCfg<2>::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<2>, ta, tb, p);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   DGQ_RETURN_LAST_ERROR();
 }
