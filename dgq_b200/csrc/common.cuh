@@ -32,6 +32,19 @@ __device__ __forceinline__ float uaq_dequant(float code, float delta, float zp) 
   return __fmul_rn(delta, __fsub_rn(code, zp));
 }
 
+// Same result as uaq_code, without the IEEE division on the common path: t = x * (1/delta) differs
+// from the correctly rounded quotient by < 2^-22 |t|, so rint(t) is the reference's rint(x / delta)
+// unless t lies within that distance of a rounding boundary (k + 1/2) -- only then is the exact
+// division evaluated (~1e-4 of the elements).  rint through the 1.5 * 2^23 magic add (exact
+// round-half-even for |t| < 2^22; larger |t| saturate the clamp anyway).
+__device__ __forceinline__ float uaq_code_rcp(float x, float delta, float inv_delta, float zp, float qmax) {
+  float t = __fmul_rn(x, inv_delta);
+  t = fminf(fmaxf(t, -4.0e6f), 4.0e6f);
+  float r = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+  if (0.5f - fabsf(__fsub_rn(t, r)) <= fabsf(t) * 4.76837158e-7f) r = rintf(__fdiv_rn(x, delta));
+  return fminf(fmaxf(r + zp, 0.0f), qmax);
+}
+
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // exact-erf GELU (torch.nn.functional.gelu default)

@@ -133,6 +133,150 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Tiled im2col producer for the hot shapes (ksize 1 or 3, stride 1, channels a multiple of 64).
+// A CTA owns an 8 x 16 output-pixel tile x 64 channels: phase 1 loads the (8+2) x (16+2) input
+// patch ONCE (concat / nearest-x2 / GroupNorm / SiLU applied once per input element instead of
+// once per tap), phase 2 emits the 9 taps -- each with its own (delta, zp) when the scales are
+// K-wise -- as 128-byte row segments of the A operand.  The quantizer runs on the reciprocal fast
+// path (uaq_code_rcp, bit-identical codes).
+constexpr int kTileH = 8, kTileW = 16, kTileC = 64;
+
+template <typename TIn, int KS, int QMODE>
+__global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p, int tiles_x, int tiles_y) {
+  constexpr int PH = kTileH + KS - 1, PW = kTileW + KS - 1;
+  __shared__ __align__(16) float patch[PH * PW][kTileC];
+  __shared__ uint8_t inside[PH * PW];
+  const int C = p.c0 + p.c1;
+  const int cblocks = C / kTileC;
+  int bid = blockIdx.x;
+  const int cb = bid % cblocks; bid /= cblocks;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
+  const int c0 = cb * kTileC;
+  const int oy0 = ty * kTileH, ox0 = tx * kTileW;
+  const int tid = threadIdx.x;
+
+  // ---- phase 1: patch -> smem (fp32, after GroupNorm + SiLU); thread = fixed 4 channels, strided pixels
+  {
+    const int c4 = (tid & 15) * 4;
+    const int c = c0 + c4;
+    float ga[4] = {1.f, 1.f, 1.f, 1.f}, gs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.gn_mean != nullptr) {
+      const int cpg = C >> 5;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = (c + i) / cpg;
+        const float mean = __ldg(p.gn_mean + b * 32 + g), rstd = __ldg(p.gn_rstd + b * 32 + g);
+        ga[i] = rstd * __ldg(p.gn_gamma + c + i);
+        gs[i] = fmaf(-mean, ga[i], __ldg(p.gn_beta + c + i));
+      }
+    }
+    const TIn* src = c < p.c0 ? static_cast<const TIn*>(p.src0) + c : static_cast<const TIn*>(p.src1) + (c - p.c0);
+    const int cs = c < p.c0 ? p.c0 : p.c1;
+    for (int pp = tid >> 4; pp < PH * PW; pp += 16) {
+      const int py = pp / PW, px = pp % PW;
+      const int iy = oy0 + py - KS / 2, ix = ox0 + px - KS / 2;
+      const bool in = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in) {
+        const int sy = p.upsample ? (iy >> 1) : iy, sx = p.upsample ? (ix >> 1) : ix;
+        const size_t pix = (static_cast<size_t>(b) * p.hs + sy) * p.ws + sx;
+        float u[4];
+        if (sizeof(TIn) == 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + pix * cs);
+          u[0] = q4.x; u[1] = q4.y; u[2] = q4.z; u[3] = q4.w;
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(src) + pix * cs);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          u[0] = lo.x; u[1] = lo.y; u[2] = hi.x; u[3] = hi.y;
+        }
+        if (p.gn_mean != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) u[i] = fmaf(u[i], ga[i], gs[i]);
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) u[i] = silu_f(u[i]);
+        }
+        v = make_float4(u[0], u[1], u[2], u[3]);
+      }
+      *reinterpret_cast<float4*>(&patch[pp][c4]) = v;
+      if ((tid & 15) == 0) inside[pp] = in ? 1 : 0;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: thread = fixed 8 channels; per tap: cache (delta, 1/delta, zp), sweep 4 pixels
+  const int cg = (tid & 7) * 8;
+  const int ps = tid >> 3;  // 0..31
+  const QuantDev& q = p.q;
+  for (int tap = 0; tap < KS * KS; ++tap) {
+    const int dy = tap / KS, dx = tap % KS;
+    const int k0 = tap * C + c0 + cg;
+    float d[8], inv[8], z[8];
+    if (QMODE == DGQ_Q_KWISE) {
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(q.delta + k0));
+      const float4 d1 = __ldg(reinterpret_cast<const float4*>(q.delta + k0 + 4));
+      const float4 z0 = __ldg(reinterpret_cast<const float4*>(q.zp + k0));
+      const float4 z1 = __ldg(reinterpret_cast<const float4*>(q.zp + k0 + 4));
+      d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+      z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+    } else if (QMODE == DGQ_Q_SCALAR) {
+      const float dd = __ldg(q.delta), zz = __ldg(q.zp), ii = __frcp_rn(dd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; inv[i] = ii; }
+    }
+#pragma unroll
+    for (int it = 0; it < (kTileH * kTileW) / 32; ++it) {
+      const int pl = ps + it * 32;
+      const int oy = oy0 + pl / kTileW, ox = ox0 + pl % kTileW;
+      if (oy >= p.ho || ox >= p.wo) continue;
+      const int pp = (pl / kTileW + dy) * PW + (pl % kTileW + dx);
+      const int m = (b * p.ho + oy) * p.wo + ox;
+      if (QMODE == DGQ_Q_ROWWISE) {
+        const int j = m % q.period;
+        const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j), ii = __frcp_rn(dd);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; inv[i] = ii; }
+      }
+      float v[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&patch[pp][cg]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&patch[pp][cg + 4]);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+      uint32_t lo = 0, hi = 0;
+      if (QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float cd = uaq_code_rcp(v[i], d[i], inv[i], z[i], q.qmax);
+          v[i] = q.emit_int ? __fsub_rn(cd, z[i]) : uaq_dequant(cd, d[i], z[i]);
+          if (i < 4) lo |= static_cast<uint32_t>(cd) << (8 * i);
+          else hi |= static_cast<uint32_t>(cd) << (8 * (i - 4));
+        }
+      }
+      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + k0) = pack8(v);
+      if (p.codes != nullptr)
+        *reinterpret_cast<uint2*>(p.codes + static_cast<size_t>(m) * (KS * KS * C) + k0) = make_uint2(lo, hi);
+    }
+  }
+}
+
+template <typename TIn, int KS>
+static void launch_conv_producer(const ProducerDev& p, cudaStream_t s) {
+  const int tiles_x = (p.wo + kTileW - 1) / kTileW, tiles_y = (p.ho + kTileH - 1) / kTileH;
+  const int grid = p.batch * tiles_y * tiles_x * ((p.c0 + p.c1) / kTileC);
+  switch (p.q.mode) {
+    case DGQ_Q_KWISE: conv_producer_kernel<TIn, KS, DGQ_Q_KWISE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    case DGQ_Q_ROWWISE: conv_producer_kernel<TIn, KS, DGQ_Q_ROWWISE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    case DGQ_Q_SCALAR: conv_producer_kernel<TIn, KS, DGQ_Q_SCALAR><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    default: conv_producer_kernel<TIn, KS, DGQ_Q_NONE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // GroupNorm statistics, stage 1: CTA (b, chunk) sums rows [chunk*rows_per, ...) per channel, folds
 // channels into the 32 groups, writes partial (sum, sumsq) to scratch[b][chunk][32][2].
 constexpr int kGnMaxC = 2560;
@@ -459,6 +603,16 @@ extern "C" int dgq_act_producer(const dgq_producer_t* a, void* stream) {
   const int64_t total = static_cast<int64_t>(p.batch) * p.ho * p.wo * (p.ldo / 8);
   const int grid = grid_for(total, 256, kNumSMs * 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // hot shapes: tiled kernel (each input element normalised once, taps emitted from smem)
+  if (a->stride == 1 && C % kTileC == 0 && a->c0 % 4 == 0 && p.ldo == K &&
+      static_cast<int64_t>(p.batch) * p.ho * p.wo * 9 * C < (int64_t(1) << 40)) {
+    if (a->ksize == 3) {
+      if (a->src_is_f32) launch_conv_producer<float, 3>(p, s); else launch_conv_producer<__half, 3>(p, s);
+    } else {
+      if (a->src_is_f32) launch_conv_producer<float, 1>(p, s); else launch_conv_producer<__half, 1>(p, s);
+    }
+    DGQ_RETURN_LAST_ERROR();
+  }
   if (a->src_is_f32) act_producer_kernel<float><<<grid, 256, 0, s>>>(p);
   else act_producer_kernel<__half><<<grid, 256, 0, s>>>(p);
   DGQ_RETURN_LAST_ERROR();

@@ -111,7 +111,8 @@ def _unfold_ref(x, k, s, delta, zp, grouped, level=256):
     return codes, dq  # (B, C*k*k, L)
 
 
-@pytest.mark.parametrize("k,s,ci,hw", [(3, 1, 32, 12), (3, 2, 32, 12), (1, 1, 64, 8), (3, 1, 320, 16)])
+@pytest.mark.parametrize("k,s,ci,hw", [(3, 1, 32, 12), (3, 2, 32, 12), (1, 1, 64, 8), (3, 1, 320, 16),
+                                       (3, 1, 64, 12), (3, 1, 128, 20), (1, 1, 128, 20), (3, 2, 64, 12)])
 @pytest.mark.parametrize("mode", ["g1", "g1u", "kwise", "rowwise"])
 def test_act_producer_codes_bit_exact(k, s, ci, hw, mode):
     from dgq_b200 import ops
