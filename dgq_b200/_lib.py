@@ -17,6 +17,7 @@ SYMBOLS = [
 
 Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE = 0, 1, 2, 3
 MAP_NONE, MAP_UNIFORM, MAP_LOG2 = 0, 1, 2
+EPI_PLAIN, EPI_GEGLU, EPI_QKV = 0, 1, 2
 
 
 class QuantT(C.Structure):
@@ -38,7 +39,9 @@ class GemmT(C.Structure):
                 ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("scale", C.c_void_p),
                 ("row_scale", C.c_void_p), ("row_period", C.c_int), ("bias", C.c_void_p), ("temb", C.c_void_p), ("rows_per_batch", C.c_int),
                 ("ld_temb", C.c_int), ("resid", C.c_void_p), ("ld_resid", C.c_int),
-                ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p), ("ep_is_f32", C.c_int)]
+                ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p), ("ep_is_f32", C.c_int),
+                ("epi", C.c_int), ("q2", QuantT), ("heads", C.c_int), ("d", C.c_int), ("dp", C.c_int),
+                ("tokens", C.c_int), ("tp", C.c_int), ("transpose", C.c_int), ("skip_first", C.c_int)]
 
 
 class AttnT(C.Structure):
@@ -47,7 +50,8 @@ class AttnT(C.Structure):
                 ("dp", C.c_int), ("scale", C.c_float), ("map_mode", C.c_int), ("real_time", C.c_int),
                 ("start_peak", C.c_int), ("delta", C.c_void_p), ("qmax", C.c_float),
                 ("row_max", C.c_void_p), ("row_sum", C.c_void_p), ("gmax", C.c_void_p),
-                ("out", C.c_void_p), ("ldo", C.c_int), ("out_is_f32", C.c_int), ("codes", C.c_void_p)]
+                ("out", C.c_void_p), ("ldo", C.c_int), ("out_is_f32", C.c_int), ("codes", C.c_void_p),
+                ("out_q", QuantT)]
 
 
 _lib = None

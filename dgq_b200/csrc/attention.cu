@@ -48,6 +48,11 @@ struct AttnDev {
   int ldo;
   int out_is_f32;
   uint8_t* codes;
+  // quantizer of the consuming QuantLayer (to_out[0]) applied to O in the epilogue
+  const float* oq_delta;
+  const float* oq_zp;
+  int oq_mode, oq_period, oq_emit_int;
+  float oq_qmax;
 };
 
 // barrier indices
@@ -357,6 +362,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
                 if (p.start_peak) f[i] = fmaf(p0, s_v0[d0 + i], f[i]);
               }
+              if (p.oq_mode != DGQ_Q_NONE) {
+                float qd[8], qz[8];
+                if (p.oq_mode == DGQ_Q_KWISE) {
+                  const int k0 = head * p.d + d0;
+                  const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.oq_delta + k0));
+                  const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.oq_delta + k0 + 4));
+                  const float4 z0 = __ldg(reinterpret_cast<const float4*>(p.oq_zp + k0));
+                  const float4 z1 = __ldg(reinterpret_cast<const float4*>(p.oq_zp + k0 + 4));
+                  qd[0] = a0.x; qd[1] = a0.y; qd[2] = a0.z; qd[3] = a0.w; qd[4] = a1.x; qd[5] = a1.y; qd[6] = a1.z; qd[7] = a1.w;
+                  qz[0] = z0.x; qz[1] = z0.y; qz[2] = z0.z; qz[3] = z0.w; qz[4] = z1.x; qz[5] = z1.y; qz[6] = z1.z; qz[7] = z1.w;
+                } else {
+                  const int j = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>((static_cast<size_t>(bb) * p.t + tq) % p.oq_period) : 0;
+                  const float dd = __ldg(p.oq_delta + j), zz = __ldg(p.oq_zp + j);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { qd[i] = dd; qz[i] = zz; }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float cd = uaq_code_rcp(f[i], qd[i], __frcp_rn(qd[i]), qz[i], p.oq_qmax);
+                  f[i] = p.oq_emit_int ? __fsub_rn(cd, qz[i]) : uaq_dequant(cd, qd[i], qz[i]);
+                }
+              }
               if (p.out_is_f32) {
                 *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
                 *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -408,6 +435,9 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   DGQ_CHECK_ARG(a->row_max != nullptr && a->row_sum != nullptr && a->gmax != nullptr);
   DGQ_CHECK_ARG(a->map_mode == DGQ_MAP_NONE || a->real_time || a->delta != nullptr);
   DGQ_CHECK_ARG(!a->real_time || a->map_mode == DGQ_MAP_LOG2);
+  DGQ_CHECK_ARG(a->out_q.mode >= DGQ_Q_NONE && a->out_q.mode <= DGQ_Q_ROWWISE);
+  DGQ_CHECK_ARG(a->out_q.mode == DGQ_Q_NONE || (a->out_q.delta != nullptr && a->out_q.zp != nullptr));
+  DGQ_CHECK_ARG(!(a->out_q.emit_int && a->out_q.mode == DGQ_Q_KWISE));
 
   AttnDev p;
   p.b = a->b; p.heads = a->heads; p.t = a->t; p.s = a->s; p.d = a->d; p.dp = a->dp;
@@ -420,6 +450,9 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   p.row_max = a->row_max; p.row_sum = a->row_sum; p.gmax = a->gmax;
   p.vt = static_cast<const __half*>(a->vt); p.sp = a->sp;
   p.out = a->out; p.ldo = a->ldo; p.out_is_f32 = a->out_is_f32; p.codes = a->codes;
+  p.oq_delta = a->out_q.delta; p.oq_zp = a->out_q.zp; p.oq_mode = a->out_q.mode;
+  p.oq_period = a->out_q.period > 0 ? a->out_q.period : 1; p.oq_emit_int = a->out_q.emit_int;
+  p.oq_qmax = a->out_q.qmax;
 
   const uint64_t bh = static_cast<uint64_t>(a->b) * a->heads;
   CUtensorMap tq, tk, tv;

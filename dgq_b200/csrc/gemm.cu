@@ -30,13 +30,24 @@ constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kStgLd = 36;                         // padded row stride (floats) of the epilogue transpose buffer
+constexpr int kEpiTab = 5;                         // per-column tables staged per tile
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
+
+struct EpiQuant {   // quantizer applied by the fused epilogues (the NEXT op's activation quantizer)
+  const float* delta;
+  const float* zp;
+  int mode, period;
+  float qmax;
+  int emit_int;
+};
 
 template <int kCtas> struct GemmCfg {
   static constexpr int kStages = kCtas == 1 ? 3 : 5;
   static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  // [2 buffers][scale | bias][256] fp32 + one [32 rows][36] fp32 transpose buffer per epilogue warp
-  static constexpr uint32_t kEpiBytes = 2 * 2 * kMaxBN * 4 + kEpiWarps * 32 * kStgLd * 4;
+  // [2 buffers][scale | bias | q.delta | 1/q.delta | q.zp][256] fp32 + one [32 rows][36] fp32 transpose
+  // buffer per epilogue warp
+  static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + kEpiWarps * 32 * kStgLd * 4;
   static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -55,6 +66,9 @@ struct GemmDev {
   int ldc;
   float* out_f32;
   int ep_is_f32;
+  EpiQuant q2;
+  // EPI_QKV geometry: GEMM row = (batch, token), column = (head, channel)
+  int heads, d, dp, tokens, tp, transpose, skip_first;
 };
 
 __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
@@ -65,7 +79,7 @@ __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
 // 256 x bn tile -- each CTA stages its own 128 rows of A and bn/2 rows of B, the leader issues the
 // MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
 // L2->smem bytes of the single-CTA tile.
-template <int kCtas>
+template <int kCtas, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
@@ -169,20 +183,25 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ------------------------------------------------------------ epilogue (warps 2..9)
     // warp -> TMEM lane quarter (warp & 3) and column half.  Per 32-column chunk: tcgen05.ld (thread
     // = row) -> row_scale * scale[n] + bias[n] -> per-warp smem transpose -> lanes across columns:
-    // + residual, 128-byte coalesced row-segment stores.  scale / bias (+ the time-embedding row when
-    // the tile lies inside one sample) are staged in smem once per tile; residual segments are
-    // prefetched one chunk ahead.
+    // + residual, 128-byte coalesced row-segment stores.  Per-column tables (scale, bias + the
+    // time-embedding row when the tile lies inside one sample, the fused quantizer's delta / zp) are
+    // staged in smem once per tile; residual segments are prefetched one chunk ahead.
+    //   EPI_GEGLU: B rows are interleaved [32 x1 | 32 gate] per 64 columns (pack time); a chunk PAIR
+    //              yields 32 features x1 * gelu(gate), quantised for ff.net.2, stored as its fp16 operand.
+    //   EPI_QKV  : quantise with aqtizer_q/k/v and store head-split ([b,h,t,dp] or V^T [b,h,dp,tp]).
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int etid = threadIdx.x - 64;
-    const int nch = p.bn >> 5;
+    constexpr int kUnit = kEpi == EPI_GEGLU ? 64 : 32;   // accumulator columns consumed per iteration
+    const int nch = p.bn / kUnit;
     const int c_begin = half == 0 ? 0 : (nch + 1) / 2;
     const int c_end = half == 0 ? (nch + 1) / 2 : nch;
     const size_t esz = p.ep_is_f32 ? 4 : 2;
     const bool temb_tile = p.temb != nullptr && (p.rows_per_batch % (kBM * kCtas)) == 0;
-    float* stg = s_epi + 2 * 2 * kMaxBN + (warp - 2) * (32 * kStgLd);
+    float* stg = s_epi + 2 * kEpiTab * kMaxBN + (warp - 2) * (32 * kStgLd);
     const int rl0 = lane >> 3;          // row (0..3) inside a group of 4 rows
     const int cq = (lane & 7) * 4;      // first of this lane's 4 columns inside the chunk
+    const EpiQuant& q2 = p.q2;
     uint32_t acc = 0, acc_phase = 0, it = 0;
     for (int tile = worker; tile < total_tiles; tile += workers, ++it) {
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
@@ -191,8 +210,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int row = warp_row0 + lane;
       const bool row_ok = row < p.m;
       const int ncol0 = n_blk * p.bn;
-      float* s_scale = s_epi + (it & 1) * 2 * kMaxBN;
+      float* s_scale = s_epi + (it & 1) * kEpiTab * kMaxBN;
       float* s_bias = s_scale + kMaxBN;
+      float* s_qd = s_bias + kMaxBN;
+      float* s_qi = s_qd + kMaxBN;
+      float* s_qz = s_qi + kMaxBN;
       for (int j = etid; j < p.bn; j += 32 * kEpiWarps) {
         const int n = ncol0 + j;
         float sc = 1.0f, bi = 0.0f;
@@ -207,11 +229,44 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         s_scale[j] = sc;
         s_bias[j] = bi;
+        if (kEpi != EPI_PLAIN && (q2.mode == DGQ_Q_KWISE || q2.mode == DGQ_Q_SCALAR)) {
+          // table slot j: EPI_QKV column j of the tile (index = channel inside the head);
+          //               EPI_GEGLU output feature j of the tile (bn / 2 of them)
+          int qi = 0;
+          bool ok = true;
+          if (q2.mode == DGQ_Q_KWISE) {
+            if (kEpi == EPI_QKV) { qi = n % p.d; ok = n < p.n; }
+            else { qi = n_blk * (p.bn >> 1) + j; ok = j < (p.bn >> 1) && 2 * qi < p.n; }
+          }
+          const float dd = ok ? __ldg(q2.delta + qi) : 1.0f;
+          s_qd[j] = dd;
+          s_qi[j] = __frcp_rn(dd);
+          s_qz[j] = ok ? __ldg(q2.zp + qi) : 0.0f;
+        }
       }
       const char* temb_row = (p.temb != nullptr && !temb_tile && row_ok)
                                  ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
                                  : nullptr;
       const float rs = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
+      // fused quantizer, row-indexed parameters (thread = row)
+      float qd_row = 1.0f, qi_row = 1.0f, qz_row = 0.0f;
+      bool q_on = kEpi != EPI_PLAIN && q2.mode != DGQ_Q_NONE;
+      int tok = 0, bat = 0;
+      if (kEpi == EPI_QKV && row_ok) { bat = row / p.tokens; tok = row - bat * p.tokens; }
+      if (kEpi != EPI_PLAIN && q2.mode == DGQ_Q_ROWWISE && row_ok) {
+        const int qi = kEpi == EPI_QKV ? max(tok - p.skip_first, 0) : row % q2.period;
+        qd_row = __ldg(q2.delta + qi);
+        qz_row = __ldg(q2.zp + qi);
+        qi_row = __frcp_rn(qd_row);
+      }
+      const bool q_skip = kEpi == EPI_QKV && p.skip_first && tok == 0;   // start-peak: token 0 bypasses
+      auto fused_quant = [&](float y, int slot) -> float {
+        if (!q_on || q_skip) return y;
+        const bool rw = q2.mode == DGQ_Q_ROWWISE;
+        const float dd = rw ? qd_row : s_qd[slot], ii = rw ? qi_row : s_qi[slot], zz = rw ? qz_row : s_qz[slot];
+        const float cd = uaq_code_rcp(y, dd, ii, zz, q2.qmax);
+        return q2.emit_int ? __fsub_rn(cd, zz) : uaq_dequant(cd, dd, zz);
+      };
       float4 t_cur[8], t_nxt[8];
       auto load_resid = [&](int c, float4 (&t)[8]) {
         const int n = ncol0 + c * 32 + cq;
@@ -232,53 +287,95 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           t[rr] = u;
         }
       };
-      if (p.resid != nullptr && c_begin < c_end) load_resid(c_begin, t_cur);
-      epi_bar_sync();                       // staged scale / bias visible
+      const bool has_resid = kEpi == EPI_PLAIN && p.resid != nullptr;
+      if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
+      epi_bar_sync();                       // staged tables visible
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        if (p.resid != nullptr && c + 1 < c_end) load_resid(c + 1, t_nxt);
-        tc_wait_ld();
-        const int j0 = c * 32;
+        const int j0 = c * kUnit;           // first accumulator column of this iteration inside the tile
+        tmem_ld_32x32(t_row + j0, r);
+        if (has_resid && c + 1 < c_end) load_resid(c + 1, t_nxt);
+        float g[32];                        // this thread's row, 32 result columns
+        if (kEpi == EPI_GEGLU) {
+          uint32_t r2[32];
+          tmem_ld_32x32(t_row + j0 + 32, r2);
+          tc_wait_ld();
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          float f[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            f[i] = fmaf(__uint_as_float(r[v * 4 + i]) * rs, s_scale[j0 + v * 4 + i], s_bias[j0 + v * 4 + i]);
-          if (temb_row != nullptr && ncol0 + j0 + v * 4 < p.n) {
-            const int n = ncol0 + j0 + v * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              f[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n + i]
-                                  : __half2float(reinterpret_cast<const __half*>(temb_row)[n + i]);
+          for (int i = 0; i < 32; ++i) {
+            const float x1 = fmaf(__uint_as_float(r[i]) * rs, s_scale[j0 + i], s_bias[j0 + i]);
+            const float x2 = fmaf(__uint_as_float(r2[i]) * rs, s_scale[j0 + 32 + i], s_bias[j0 + 32 + i]);
+            g[i] = fused_quant(x1 * gelu_erf_f(x2), c * 32 + i);
           }
-          *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(f[0], f[1], f[2], f[3]);
-        }
-        __syncwarp();
-        const int n = ncol0 + j0 + cq;
-        if (n < p.n) {
+        } else {
+          tc_wait_ld();
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int rl = rr * 4 + rl0;
-            const int grow = warp_row0 + rl;
-            if (grow < p.m) {
-              float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
-              if (p.resid != nullptr) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
-              const size_t o = static_cast<size_t>(grow) * p.ldc + n;
-              if (p.out != nullptr) {
-                const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
-                *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-              }
-              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+          for (int i = 0; i < 32; ++i)
+            g[i] = fmaf(__uint_as_float(r[i]) * rs, s_scale[j0 + i], s_bias[j0 + i]);
+          if (temb_row != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int n = ncol0 + j0 + i;
+              if (n < p.n)
+                g[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n]
+                                    : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
             }
           }
+          if (kEpi == EPI_QKV) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) g[i] = fused_quant(g[i], j0 + i);
+          }
         }
-        __syncwarp();
-        if (p.resid != nullptr) {
+        if (kEpi == EPI_QKV && p.transpose) {
+          // V^T [b, heads, dp, tp]: for a fixed column the 32 lanes hold 32 consecutive tokens
+          if (row_ok) {
+            int n = ncol0 + j0;
+            int hh = n / p.d, dd = n - hh * p.d;
+            __half* base = p.out + (static_cast<size_t>(bat) * p.heads) * p.dp * p.tp + tok;
+#pragma unroll
+            for (int i = 0; i < 32; ++i, ++n) {
+              if (n < p.n) base[(static_cast<size_t>(hh) * p.dp + dd) * p.tp] = __float2half_rn(g[i]);
+              if (++dd == p.d) { dd = 0; ++hh; }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+          __syncwarp();
+          // result column of this lane's 4 values: GEGLU feature index, otherwise the GEMM column
+          const int n = kEpi == EPI_GEGLU ? n_blk * (p.bn >> 1) + c * 32 + cq : ncol0 + j0 + cq;
+          const int n_lim = kEpi == EPI_GEGLU ? (p.n >> 1) : p.n;
+          if (n < n_lim) {
+            int hh = 0, dd = 0;
+            if (kEpi == EPI_QKV) { hh = n / p.d; dd = n - hh * p.d; }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int rl = rr * 4 + rl0;
+              const int grow = warp_row0 + rl;
+              if (grow < p.m) {
+                float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+                if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+                size_t o;
+                if (kEpi == EPI_QKV) {
+                  const int gb = grow / p.tokens, gt = grow - gb * p.tokens;
+                  o = ((static_cast<size_t>(gb) * p.heads + hh) * p.tokens + gt) * p.dp + dd;
+                } else {
+                  o = static_cast<size_t>(grow) * p.ldc + n;
+                }
+                if (p.out != nullptr) {
+                  const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                  *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                }
+                if (kEpi == EPI_PLAIN && p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        if (has_resid) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
         }
@@ -333,16 +430,49 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols
 }
 
 // N tile: the largest multiple of 32 (<= 256) that wastes the least padded work
-static int pick_bn(int n) {
-  int best = 32;
+static int pick_bn(int n, int step) {
+  int best = step;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
+  for (int bn = 256; bn >= step; bn -= step) {
     const int tiles = (n + bn - 1) / bn;
     // padded columns, with a mild penalty for narrow tiles (A re-read from smem per MMA)
     const double cost = static_cast<double>(tiles) * bn * (1.0 + 16.0 / bn);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+template <int kCtas, int kEpi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, cudaStream_t s) {
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<kCtas>::kSmem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  if (kCtas == 1) {
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    gemm_f16_kernel<kCtas, kEpi><<<grid, kGemmThreads, GemmCfg<kCtas>::kSmem, s>>>(ta, tb, p);
+  } else {
+    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = GemmCfg<kCtas>::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtas, kEpi>, ta, tb, p);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  DGQ_RETURN_LAST_ERROR();
 }
 
 }  // namespace dgq
@@ -355,22 +485,30 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   DGQ_CHECK_ARG(a->out != nullptr || a->out_f32 != nullptr);
   DGQ_CHECK_ARG(a->temb == nullptr || (a->rows_per_batch > 0 && a->ld_temb % 8 == 0));
   DGQ_CHECK_ARG(a->resid == nullptr || a->ld_resid % 8 == 0);
+  DGQ_CHECK_ARG(a->epi >= DGQ_EPI_PLAIN && a->epi <= DGQ_EPI_QKV);
+  if (a->epi != DGQ_EPI_PLAIN) {
+    const dgq_quant_t& q = a->q2;
+    DGQ_CHECK_ARG(a->out != nullptr && a->resid == nullptr);
+    DGQ_CHECK_ARG(q.mode >= DGQ_Q_NONE && q.mode <= DGQ_Q_ROWWISE);
+    DGQ_CHECK_ARG(q.mode == DGQ_Q_NONE || (q.delta != nullptr && q.zp != nullptr));
+    DGQ_CHECK_ARG(q.mode != DGQ_Q_ROWWISE || q.period > 0);
+    DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE));
+  }
+  if (a->epi == DGQ_EPI_GEGLU) DGQ_CHECK_ARG(a->n % 64 == 0 && a->ldc >= a->n / 2);
+  if (a->epi == DGQ_EPI_QKV) {
+    DGQ_CHECK_ARG(a->heads > 0 && a->d > 0 && a->d % 8 == 0 && a->dp >= a->d && a->dp % 8 == 0);
+    DGQ_CHECK_ARG(a->n == a->heads * a->d && a->tokens > 0 && a->m % a->tokens == 0);
+    DGQ_CHECK_ARG(!a->transpose || (a->tp >= a->tokens && a->tp % 8 == 0));
+  }
 
-  static bool attr_set = false;
-  static int force_ctas = 0;   // DGQ_GEMM_CTAS=1|2 pins the variant (benchmarking); default: by problem size
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<1>::kSmem);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaFuncSetAttribute(gemm_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmem);
-    if (e != cudaSuccess) return static_cast<int>(e);
+  static int force_ctas = -1;   // DGQ_GEMM_CTAS=1|2 pins the variant (benchmarking); default: by problem size
+  if (force_ctas < 0) {
     const char* env = getenv("DGQ_GEMM_CTAS");
-    if (env != nullptr) force_ctas = atoi(env);
-    attr_set = true;
+    force_ctas = env != nullptr ? atoi(env) : 0;
   }
   GemmDev p;
   p.m = a->m; p.n = a->n; p.k = a->k;
-  p.bn = pick_bn(a->n);
+  p.bn = pick_bn(a->n, a->epi == DGQ_EPI_GEGLU ? 64 : 32);
   p.n_tiles = (a->n + p.bn - 1) / p.bn;
   // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; small problems keep
   // 128-row tiles on single CTAs so more SMs get a tile
@@ -384,6 +522,9 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   p.resid = a->resid; p.ld_resid = a->ld_resid;
   p.out = static_cast<__half*>(a->out); p.ldc = a->ldc; p.out_f32 = a->out_f32;
   p.ep_is_f32 = a->ep_is_f32;
+  p.q2 = EpiQuant{a->q2.delta, a->q2.zp, a->q2.mode, a->q2.period > 0 ? a->q2.period : 1, a->q2.qmax, a->q2.emit_int};
+  p.heads = a->heads; p.d = a->d > 0 ? a->d : 1; p.dp = a->dp; p.tokens = a->tokens > 0 ? a->tokens : 1;
+  p.tp = a->tp; p.transpose = a->transpose; p.skip_first = a->skip_first;
 
   CUtensorMap ta, tb;
   int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM);
@@ -392,27 +533,13 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn / ctas);
   if (rc != 0) return rc;
 
-  const int tiles = p.m_tiles * p.n_tiles;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (ctas == 1) {
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_f16_kernel<1><<<grid, kGemmThreads, GemmCfg<1>::kSmem, s>>>(ta, tb, p);
-  } else {
-    const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs, 1, 1);
-    cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = GemmCfg<2>::kSmem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<2>, ta, tb, p);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU>(ta, tb, p, s);
+    if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV>(ta, tb, p, s);
+    return launch_gemm<1, EPI_PLAIN>(ta, tb, p, s);
   }
-  DGQ_RETURN_LAST_ERROR();
+  if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<2, EPI_GEGLU>(ta, tb, p, s);
+  if (a->epi == DGQ_EPI_QKV) return launch_gemm<2, EPI_QKV>(ta, tb, p, s);
+  return launch_gemm<2, EPI_PLAIN>(ta, tb, p, s);
 }

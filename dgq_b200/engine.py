@@ -77,15 +77,15 @@ def _exact(q: ops.QParam) -> bool:
 
 
 def _gemm(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, temb=None, rows_per_batch=0, resid=None,
-          want_f32=None):
+          want_f32=None, **fused):
     """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q`."""
-    operand, scale, bias, n_pad = ql.packed()
+    operand, scale, bias, n_pad = ql.packed(geglu=fused.get("epi") == ops.EPI_GEGLU)
     if want_f32 is None:
         want_f32 = ops.ACT_DTYPE == torch.float32
     ex = _exact(q)
     return ops.gemm(a_op, operand, n_pad, scale=scale, bias=bias, temb=temb, rows_per_batch=rows_per_batch,
                     resid=resid, want_f32=want_f32, k=operand.shape[1],
-                    row_scale=q.delta if ex else None, row_period=q.period if ex else 1)
+                    row_scale=q.delta if ex else None, row_period=q.period if ex else 1, **fused)
 
 
 def conv(ql, x: Act, *, x2: Optional[Act] = None, upsample: bool = False, gn=None, act: int = 0,
@@ -202,8 +202,22 @@ def _attn_qparam(qt, attn, device):
     return qt.qparam(device)
 
 
+FUSE_EPILOGUES = True  # GEGLU / head-split+quantize / to_out quantize inside the producing kernels
+
+
+def _map_args(attn, dev, sp):
+    """keyword arguments of ops.attention for attn's softmax-map quantizer (aqtizer_w)."""
+    wq = attn.aqtizer_w
+    if hasattr(wq, "real_time"):  # T2ILogQuantizer
+        return dict(map_mode=ops.MAP_LOG2, real_time=wq.real_time, start_peak=sp,
+                    delta=None if wq.real_time else wq.static_delta(dev), qmax=float(wq.level - 1))
+    return dict(map_mode=ops.MAP_UNIFORM, start_peak=sp, delta=wq.qparam(dev).delta,  # always_zero uniform
+                qmax=float(wq.level - 1))
+
+
 def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, t: int, s: int) -> torch.Tensor:
-    """q [b*t, C], k/v [b*s, C] fp16 -> [b*t, C]: quantise + head split, fused two-pass attention."""
+    """q [b*t, C], k/v [b*s, C] -> [b*t, C]: quantise + head split, fused two-pass attention
+    (stand-alone / unfused form: separate dgq_qkv_pack launches)."""
     dev = q.device
     heads, d = attn.num_heads, attn.head_dim
     dp = (d + 63) // 64 * 64
@@ -217,26 +231,37 @@ def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: i
     if not use_aq:
         out, _ = ops.attention(qq, kk, vv, d, map_mode=ops.MAP_NONE, out_dtype=ops.ACT_DTYPE)
         return out
-    wq = attn.aqtizer_w
-    if hasattr(wq, "real_time"):  # T2ILogQuantizer
-        delta = None if wq.real_time else wq.static_delta(dev)
-        out, _ = ops.attention(qq, kk, vv, d, map_mode=ops.MAP_LOG2, real_time=wq.real_time, start_peak=sp,
-                               delta=delta, qmax=float(wq.level - 1), out_dtype=ops.ACT_DTYPE)
-    else:                          # UniformAffineQuantizer(always_zero=True)
-        delta = wq.qparam(dev).delta
-        out, _ = ops.attention(qq, kk, vv, d, map_mode=ops.MAP_UNIFORM, start_peak=sp, delta=delta,
-                               qmax=float(wq.level - 1), out_dtype=ops.ACT_DTYPE)
+    out, _ = ops.attention(qq, kk, vv, d, out_dtype=ops.ACT_DTYPE, **_map_args(attn, dev, sp))
     return out
 
 
 def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torch.Tensor]) -> torch.Tensor:
     """Attention_forward given the three already-quantised projection inputs (operands xq/xk/xv
     written under quantizers qs = [q_to_q, q_to_k, q_to_v])."""
-    q = linear(attn.to_q, xq, qs[0])
-    k = linear(attn.to_k, xk, qs[1])
-    v = linear(attn.to_v, xv, qs[2])
-    o = attention_core(attn, q, k, v, b, t, s)
-    return linear(attn.to_out[0], *quant_rows(o, attn.to_out[0]), resid=resid)
+    if not FUSE_EPILOGUES:
+        q = linear(attn.to_q, xq, qs[0])
+        k = linear(attn.to_k, xk, qs[1])
+        v = linear(attn.to_v, xv, qs[2])
+        o = attention_core(attn, q, k, v, b, t, s)
+        return linear(attn.to_out[0], *quant_rows(o, attn.to_out[0]), resid=resid)
+    dev = xq.device
+    heads, d = attn.num_heads, attn.head_dim
+    dp = (d + 63) // 64 * 64
+    use_aq = bool(getattr(attn, "use_aq", False))
+    sp = bool(getattr(attn, "start_peak", False)) and use_aq
+    aq = [(_attn_qparam(getattr(attn, n), attn, dev) if use_aq else ops.NOQ) for n in ("aqtizer_q", "aqtizer_k", "aqtizer_v")]
+    ops_qkv = []
+    for ql, x, qin, q2, tok, tr, skip in ((attn.to_q, xq, qs[0], aq[0], t, False, False),
+                                         (attn.to_k, xk, qs[1], aq[1], s, False, sp),
+                                         (attn.to_v, xv, qs[2], aq[2], s, True, False)):
+        dst = ops.qkv_dest(b, tok, heads, d, dp, tr, dev)
+        _gemm(ql, x, qin, epi=ops.EPI_QKV, q2=q2, out=dst,
+              qkv=(heads, d, dp, tok, (tok + 7) // 8 * 8, tr, skip))
+        ops_qkv.append(dst)
+    qo = attn.to_out[0].act_qparam(dev)
+    margs = _map_args(attn, dev, sp) if use_aq else dict(map_mode=ops.MAP_NONE)
+    o, _ = ops.attention(ops_qkv[0], ops_qkv[1], ops_qkv[2], d, out_q=qo, out_emit_int=_exact(qo), **margs)
+    return linear(attn.to_out[0], o, qo, resid=resid)
 
 
 def _ctx_operand(ctx: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
@@ -269,9 +294,12 @@ def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor]) -> Act:
     proj, out = ff.net[0].proj, ff.net[2]
     qp = proj.act_qparam(dev)
     x3 = ops.ln_quant(x, _f32(blk.norm3.weight), _f32(blk.norm3.bias), blk.norm3.eps, [qp], emit_int=EXACT_INT)[0]
-    g = linear(proj, x3, qp)
     qo = out.act_qparam(dev)
-    x = linear(out, ops.geglu_quant(g, qo, emit_int=EXACT_INT), qo, resid=x)
+    if FUSE_EPILOGUES and proj.out_features % 64 == 0:
+        g = _gemm(proj, x3, qp, epi=ops.EPI_GEGLU, q2=qo, q2_emit_int=EXACT_INT)
+    else:
+        g = ops.geglu_quant(linear(proj, x3, qp), qo, emit_int=EXACT_INT)
+    x = linear(out, g, qo, resid=x)
     return Act(x, h.b, h.h, h.w)
 
 

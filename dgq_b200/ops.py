@@ -13,7 +13,8 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE, MAP_NONE, MAP_UNIFORM, MAP_LOG2  # noqa: F401
+from ._lib import (Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE, MAP_NONE, MAP_UNIFORM, MAP_LOG2,  # noqa: F401
+                   EPI_PLAIN, EPI_GEGLU, EPI_QKV)
 
 LAUNCHES = 0  # kernels launched through this module (some entry points launch two)
 
@@ -227,12 +228,20 @@ def geglu_quant(x: torch.Tensor, q: QParam, emit_int: bool = False) -> torch.Ten
 
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, temb=None, rows_per_batch: int = 0,
          resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None,
-         row_scale: Optional[torch.Tensor] = None, row_period: int = 1):
+         row_scale: Optional[torch.Tensor] = None, row_period: int = 1, epi: int = L.EPI_PLAIN,
+         q2: QParam = NOQ, q2_emit_int: bool = False, qkv: Optional[tuple] = None):
     """a fp16 [m, lda], b fp16 [n_pad, ldb] -> [m, n] (n multiple of 8), fp32 if want_f32 (or `out`
-    is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32)."""
+    is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32).
+    epi = EPI_GEGLU: b rows interleaved (pack_weight geglu=True); returns the fp16 operand [m, n/2] of
+    ff.net.2 quantised with q2.  epi = EPI_QKV: `out` is the head-split destination, qkv =
+    (heads, d, dp, tokens, tp, transpose, skip_first)."""
     m = a.shape[0]
     k = k or min(a.shape[1], b.shape[1])
-    if out is None:
+    if epi == L.EPI_GEGLU:
+        out = torch.empty(m, n // 2, dtype=torch.float16, device=a.device)
+    elif epi == L.EPI_QKV:
+        assert out is not None and out.dtype == torch.float16 and qkv is not None
+    elif out is None:
         out = torch.empty(m, n, dtype=torch.float32 if want_f32 else torch.float16, device=a.device)
     o32 = out.dtype == torch.float32
     ep32 = 0
@@ -241,13 +250,24 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
             ep32 = _is32(e)
     if temb is not None and resid is not None and _is32(temb) != _is32(resid):
         raise TypeError("temb and resid must have the same dtype")
+    heads, d, dp, tokens, tp, transpose, skip_first = qkv if qkv is not None else (0, 0, 0, 0, 0, 0, 0)
+    ldc = out.stride(0) if epi != L.EPI_QKV else 8
     g = L.GemmT(_p(a), a.stride(0), _p(b), b.stride(0), m, n, k, _p(scale), _p(row_scale), row_period, _p(bias),
                 _p(temb), rows_per_batch,
                 temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
-                None if o32 else _p(out), out.stride(0), _p(out) if o32 else None, ep32)
+                None if o32 else _p(out), ldc, _p(out) if o32 else None, ep32,
+                epi, q2.struct(q2_emit_int and q2.exact), heads, d, dp, tokens, tp, int(transpose), int(skip_first))
     L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
     _count()
     return out
+
+
+def qkv_dest(b: int, t: int, heads: int, d: int, dp: int, transpose: bool, device) -> torch.Tensor:
+    """destination of an EPI_QKV GEMM (zero-filled only when it has padding the kernel does not write)"""
+    tp = (t + 7) // 8 * 8
+    shape = (b, heads, dp, tp) if transpose else (b, heads, t, dp)
+    padded = dp != d or (transpose and tp != t)
+    return (torch.zeros if padded else torch.empty)(shape, dtype=torch.float16, device=device)
 
 
 def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, transpose: bool = False,
@@ -263,11 +283,14 @@ def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, tr
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map_mode: int, real_time: bool = False,
               start_peak: bool = False, delta: Optional[torch.Tensor] = None, qmax: float = 255.0,
-              out: Optional[torch.Tensor] = None, want_codes: bool = False, out_dtype=torch.float16):
+              out: Optional[torch.Tensor] = None, want_codes: bool = False, out_dtype=torch.float16,
+              out_q: Optional[QParam] = None, out_emit_int: bool = False):
     """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta[, codes])."""
     b, heads, t, dp = q.shape
     s, sp = k.shape[2], vt.shape[3]
     dev = q.device
+    if out_q is not None:     # fused quantizer of the consumer: the result IS its fp16 GEMM operand
+        out_dtype = torch.float16
     if out is None:
         out = torch.empty(b * t, heads * d, dtype=out_dtype, device=dev)
     row_max = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
@@ -276,7 +299,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map
     codes = torch.zeros(b, heads, t, s, dtype=torch.uint8, device=dev) if want_codes else None
     a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
                 int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0),
-                _is32(out), _p(codes))
+                _is32(out), _p(codes), (out_q or NOQ).struct(out_emit_int and (out_q or NOQ).exact))
     L.check(L.lib().dgq_attention(C.byref(a), _stream()), "dgq_attention")
     _count(2)
     return (out, gmax[:1], codes) if want_codes else (out, gmax[:1])

@@ -265,22 +265,24 @@ class QuantLayer(nn.Module):
                 + torch.arange(kk, device=device).view(kk, 1)).reshape(-1)
 
     # -- packed weights (K2: once, not per forward) -----------------------------------------
-    def packed(self):
-        """(operand fp16 [n_pad, K], scale fp32 [n_pad] | None, bias fp32 [n_pad] | None, n_pad)."""
+    def packed(self, geglu: bool = False):
+        """(operand fp16 [n_pad, K], scale fp32 [n_pad] | None, bias fp32 [n_pad] | None, n_pad).
+        geglu: rows interleaved for the fused GEGLU epilogue (cached separately)."""
         w = self.w if self.use_wq else self.original_w
         b = self.b if self.use_wq else self.original_b
         _need_cuda(w, "QuantLayer weights")
         wq = self.wqtizer
         alpha = getattr(wq, "alpha", None)
-        key = (self.use_wq, id(w), w._version, None if b is None else (id(b), b._version))
+        key = (self.use_wq, id(w), w._version, None if b is None else (id(b), b._version), geglu)
         if self.use_wq:
             if wq.delta is None:
                 wq.delta, wq.zero_point = channel_minmax(self.w, wq.level)  # reference :253-264
                 wq.init = True
             key += (id(wq.delta), wq.delta._version, id(wq.zero_point), wq.zero_point._version,
                     None if alpha is None else (id(alpha), alpha._version))
-        if self._pack is not None and self._pack[0] == key:
-            return self._pack[1]
+        hit = self._pack.get(geglu) if self._pack else None
+        if hit is not None and hit[0] == key:
+            return hit[1]
         dev = w.device
         n = w.shape[0]
         n_pad = (n + 7) // 8 * 8
@@ -297,8 +299,21 @@ class QuantLayer(nn.Module):
         if b is not None:
             bias = torch.zeros(n_pad, dtype=torch.float32, device=dev)
             bias[:n] = b.detach().to(dev, torch.float32)
-        self._pack = (key, (operand, scale, bias, n_pad))
-        return self._pack[1]
+        if geglu:
+            # GEGLU projection feeding the fused epilogue (DGQ_EPI_GEGLU): GEMM columns are re-ordered
+            # [32 x1 | 32 gate] per 64, so one epilogue thread holds x1 and its gate together
+            f = n // 2
+            if n % 64 or n_pad != n:
+                raise ValueError("GEGLU interleave needs 2f to be a multiple of 64")
+            i = torch.arange(n, device=dev)
+            perm = (i // 64) * 32 + i % 32 + ((i % 64) >= 32) * f
+            operand = operand[perm].contiguous()
+            scale = None if scale is None else scale[perm].contiguous()
+            bias = None if bias is None else bias[perm].contiguous()
+        if not self._pack:
+            self._pack = {}
+        self._pack[geglu] = (key, (operand, scale, bias, n_pad))
+        return self._pack[geglu][1]
 
     def packed_int4(self):
         """The W4 checkpoint payload: two codes per byte + per-channel (delta, zp) -- 0.5 B/weight."""

@@ -143,7 +143,24 @@ typedef struct {
   void* out; int ldc;  /* fp16 result, optional */
   float* out_f32;      /* fp32 result, optional (at least one of out / out_f32) */
   int ep_is_f32;       /* dtype of temb / resid */
+  /* ---- fused epilogues: the GEMM result never reaches HBM in fp32, the NEXT op's fp16 operand is
+   *      written instead (quantised with that op's activation quantizer q2; emit_int allowed).
+   * DGQ_EPI_GEGLU : ff.net.0.proj (diffusers_rewrite/sd.py:210-218) -> x1 * gelu_erf(gate), quantised
+   *                 for ff.net.2; B rows must be interleaved [32 x1 | 32 gate] per 64 GEMM columns
+   *                 (dgq_b200 does this at pack time), n = 2f, out = fp16 [m, ldc >= f], resid unused.
+   * DGQ_EPI_QKV   : to_q / to_k / to_v (sd.py:171-180) -> aqtizer_q/k/v -> head-split operand of
+   *                 dgq_attention: out = fp16 [b, heads, tokens, dp] (transpose == 0) or V^T
+   *                 [b, heads, dp, tp] (transpose == 1); m = b * tokens, n = heads * d.  q2.mode KWISE
+   *                 indexes the channel inside the head, ROWWISE the token (minus skip_first);
+   *                 skip_first == 1: token 0 bypasses the quantizer (start-peak).  Padding of the
+   *                 destination (dp > d, tp > tokens) is not written: pre-zero it.                  */
+  int epi;             /* DGQ_EPI_* */
+  dgq_quant_t q2;
+  int heads, d, dp, tokens, tp, transpose, skip_first;
 } dgq_gemm_t;
+#define DGQ_EPI_PLAIN 0
+#define DGQ_EPI_GEGLU 1
+#define DGQ_EPI_QKV 2
 int dgq_gemm_f16(const dgq_gemm_t* host_args, void* stream);
 
 /* ---- attention with quantised operands and quantised softmax map
@@ -177,6 +194,9 @@ typedef struct {
   int ldo;
   int out_is_f32;
   uint8_t* codes;       /* optional u8 [b, heads, t, s]: integer codes of the map (verification only) */
+  dgq_quant_t out_q;    /* quantizer of the consuming QuantLayer (to_out[0], quant/quant_layer.py:640-641)
+                           applied to O before the store: KWISE index = column, ROWWISE = row % period;
+                           mode NONE: O is stored as is */
 } dgq_attn_t;
 int dgq_attention(const dgq_attn_t* host_args, void* stream);
 
