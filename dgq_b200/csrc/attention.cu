@@ -378,11 +378,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
                   for (int i = 0; i < 8; ++i) { qd[i] = dd; qz[i] = zz; }
                 }
+                float qi[8], cd[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float cd = uaq_code_rcp(f[i], qd[i], __frcp_rn(qd[i]), qz[i], p.oq_qmax);
-                  f[i] = p.oq_emit_int ? __fsub_rn(cd, qz[i]) : uaq_dequant(cd, qd[i], qz[i]);
-                }
+                for (int i = 0; i < 8; ++i) qi[i] = __frcp_rn(qd[i]);
+                uaq_codes_rcp<8>(f, qd, qi, qz, p.oq_qmax, cd);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  f[i] = p.oq_emit_int ? __fsub_rn(cd[i], qz[i]) : uaq_dequant(cd[i], qd[i], qz[i]);
               }
               if (p.out_is_f32) {
                 *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);

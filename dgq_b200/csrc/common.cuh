@@ -37,19 +37,61 @@ __device__ __forceinline__ float uaq_dequant(float code, float delta, float zp) 
 // unless t lies within that distance of a rounding boundary (k + 1/2) -- only then is the exact
 // division evaluated (~1e-4 of the elements).  rint through the 1.5 * 2^23 magic add (exact
 // round-half-even for |t| < 2^22; larger |t| saturate the clamp anyway).
-__device__ __forceinline__ float uaq_code_rcp(float x, float delta, float inv_delta, float zp, float qmax) {
+// N values at a time: the common path is branch-free (independent chains interleave), the rare exact
+// path is ONE branch per batch.
+__device__ __forceinline__ float uaq_round_rcp(float x, float inv_delta, bool& near_tie) {
   float t = __fmul_rn(x, inv_delta);
   t = fminf(fmaxf(t, -4.0e6f), 4.0e6f);
-  float r = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
-  if (0.5f - fabsf(__fsub_rn(t, r)) <= fabsf(t) * 4.76837158e-7f) r = rintf(__fdiv_rn(x, delta));
-  return fminf(fmaxf(r + zp, 0.0f), qmax);
+  const float r = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+  near_tie |= (0.5f - fabsf(__fsub_rn(t, r))) <= fabsf(t) * 4.76837158e-7f;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void uaq_codes_rcp(const float (&x)[N], const float (&delta)[N], const float (&inv)[N],
+                                              const float (&zp)[N], float qmax, float (&code)[N]) {
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) code[i] = uaq_round_rcp(x[i], inv[i], near_tie);
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) code[i] = rintf(__fdiv_rn(x[i], delta[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) code[i] = fminf(fmaxf(code[i] + zp[i], 0.0f), qmax);
+}
+// one (delta, zp) for the whole batch
+template <int N>
+__device__ __forceinline__ void uaq_codes_rcp1(const float (&x)[N], float delta, float inv, float zp, float qmax,
+                                               float (&code)[N]) {
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) code[i] = uaq_round_rcp(x[i], inv, near_tie);
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) code[i] = rintf(__fdiv_rn(x[i], delta));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) code[i] = fminf(fmaxf(code[i] + zp, 0.0f), qmax);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
-// exact-erf GELU (torch.nn.functional.gelu default)
+// erf-GELU (torch.nn.functional.gelu default), branch-free: erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7 absolute, the rounding level of fp32 erf itself), 2 MUFU + ~12 FP32 ops
 __device__ __forceinline__ float gelu_erf_f(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float y = x * 0.70710678118654752f;
+  const float ay = fabsf(y);
+  const float t = __frcp_rn(fmaf(0.3275911f, ay, 1.0f));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  pl *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ay * ay * -1.4426950408889634f));
+  const float erfc_abs = pl * e;                              // erfc(|y|)
+  const float cdf2 = y < 0.0f ? erfc_abs : 2.0f - erfc_abs;   // 1 + erf(y), no cancellation in the tail
+  return 0.5f * x * cdf2;
 }
 
 union Half8 {

@@ -252,7 +252,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       float qd_row = 1.0f, qi_row = 1.0f, qz_row = 0.0f;
       bool q_on = kEpi != EPI_PLAIN && q2.mode != DGQ_Q_NONE;
       int tok = 0, bat = 0;
-      if (kEpi == EPI_QKV && row_ok) { bat = row / p.tokens; tok = row - bat * p.tokens; }
+      int wbat = 0, wtok = 0;               // (batch, token) of the warp's first row
+      if (kEpi == EPI_QKV) {
+        wbat = warp_row0 / p.tokens; wtok = warp_row0 - wbat * p.tokens;
+        bat = wbat; tok = wtok + lane;
+        while (tok >= p.tokens) { tok -= p.tokens; ++bat; }
+      }
       if (kEpi != EPI_PLAIN && q2.mode == DGQ_Q_ROWWISE && row_ok) {
         const int qi = kEpi == EPI_QKV ? max(tok - p.skip_first, 0) : row % q2.period;
         qd_row = __ldg(q2.delta + qi);
@@ -260,12 +265,46 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         qi_row = __frcp_rn(qd_row);
       }
       const bool q_skip = kEpi == EPI_QKV && p.skip_first && tok == 0;   // start-peak: token 0 bypasses
-      auto fused_quant = [&](float y, int slot) -> float {
-        if (!q_on || q_skip) return y;
+      // quantise 32 results of this thread's row with the fused quantizer; table slots slot0 .. slot0 + 31
+      auto fused_quant32 = [&](float (&g)[32], int slot0) {
+        if (!q_on || q_skip) return;
         const bool rw = q2.mode == DGQ_Q_ROWWISE;
-        const float dd = rw ? qd_row : s_qd[slot], ii = rw ? qi_row : s_qi[slot], zz = rw ? qz_row : s_qz[slot];
-        const float cd = uaq_code_rcp(y, dd, ii, zz, q2.qmax);
-        return q2.emit_int ? __fsub_rn(cd, zz) : uaq_dequant(cd, dd, zz);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float x[8], dd[8], ii[8], zz[8], cd[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = g[v * 8 + i];
+          if (rw) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dd[i] = qd_row; ii[i] = qi_row; zz[i] = qz_row; }
+          } else {
+#pragma unroll
+            for (int h4 = 0; h4 < 2; ++h4) {
+              const float4 a = *reinterpret_cast<const float4*>(s_qd + slot0 + v * 8 + h4 * 4);
+              const float4 b = *reinterpret_cast<const float4*>(s_qi + slot0 + v * 8 + h4 * 4);
+              const float4 c = *reinterpret_cast<const float4*>(s_qz + slot0 + v * 8 + h4 * 4);
+              dd[h4 * 4] = a.x; dd[h4 * 4 + 1] = a.y; dd[h4 * 4 + 2] = a.z; dd[h4 * 4 + 3] = a.w;
+              ii[h4 * 4] = b.x; ii[h4 * 4 + 1] = b.y; ii[h4 * 4 + 2] = b.z; ii[h4 * 4 + 3] = b.w;
+              zz[h4 * 4] = c.x; zz[h4 * 4 + 1] = c.y; zz[h4 * 4 + 2] = c.z; zz[h4 * 4 + 3] = c.w;
+            }
+          }
+          uaq_codes_rcp<8>(x, dd, ii, zz, q2.qmax, cd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            g[v * 8 + i] = q2.emit_int ? __fsub_rn(cd[i], zz[i]) : uaq_dequant(cd[i], dd[i], zz[i]);
+        }
+      };
+      // g[i] = acc[i] * row_scale * scale[n] + bias[n] for 32 consecutive tile columns j0 ..
+      auto affine32 = [&](const uint32_t (&r)[32], int j0, float (&g)[32]) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
+          const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
+          g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
+          g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
+          g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
+          g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+        }
       };
       float4 t_cur[8], t_nxt[8];
       auto load_resid = [&](int c, float4 (&t)[8]) {
@@ -303,17 +342,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           uint32_t r2[32];
           tmem_ld_32x32(t_row + j0 + 32, r2);
           tc_wait_ld();
+          float x2[32];
+          affine32(r, j0, g);
+          affine32(r2, j0 + 32, x2);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x1 = fmaf(__uint_as_float(r[i]) * rs, s_scale[j0 + i], s_bias[j0 + i]);
-            const float x2 = fmaf(__uint_as_float(r2[i]) * rs, s_scale[j0 + 32 + i], s_bias[j0 + 32 + i]);
-            g[i] = fused_quant(x1 * gelu_erf_f(x2), c * 32 + i);
-          }
+          for (int i = 0; i < 32; ++i) g[i] *= gelu_erf_f(x2[i]);
+          fused_quant32(g, c * 32);
         } else {
           tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            g[i] = fmaf(__uint_as_float(r[i]) * rs, s_scale[j0 + i], s_bias[j0 + i]);
+          affine32(r, j0, g);
           if (temb_row != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -323,10 +360,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                     : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
             }
           }
-          if (kEpi == EPI_QKV) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) g[i] = fused_quant(g[i], j0 + i);
-          }
+          if (kEpi == EPI_QKV) fused_quant32(g, j0);
         }
         if (kEpi == EPI_QKV && p.transpose) {
           // V^T [b, heads, dp, tp]: for a fixed column the 32 lanes hold 32 consecutive tokens
@@ -360,7 +394,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
                 size_t o;
                 if (kEpi == EPI_QKV) {
-                  const int gb = grow / p.tokens, gt = grow - gb * p.tokens;
+                  int gb = wbat, gt = wtok + rl;          // (batch, token) of row grow, without a division
+                  while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
                   o = ((static_cast<size_t>(gb) * p.heads + hh) * p.tokens + gt) * p.dp + dd;
                 } else {
                   o = static_cast<size_t>(grow) * p.ldc + n;

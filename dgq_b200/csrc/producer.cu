@@ -51,9 +51,13 @@ __device__ __forceinline__ void quant8(const QuantDev& q, float (&v)[8], int k0,
     for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; }
   }
   uint32_t lo = 0, hi = 0;
+  float inv[8], cd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+  uaq_codes_rcp<8>(v, d, inv, z, q.qmax, cd);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float c = uaq_code(v[i], d[i], z[i], q.qmax);
+    const float c = cd[i];
     v[i] = q.emit_int ? __fsub_rn(c, z[i]) : uaq_dequant(c, d[i], z[i]);
     if (i < 4) lo |= static_cast<uint32_t>(c) << (8 * i);
     else hi |= static_cast<uint32_t>(c) << (8 * (i - 4));
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
 // patch ONCE (concat / nearest-x2 / GroupNorm / SiLU applied once per input element instead of
 // once per tap), phase 2 emits the 9 taps -- each with its own (delta, zp) when the scales are
 // K-wise -- as 128-byte row segments of the A operand.  The quantizer runs on the reciprocal fast
-// path (uaq_code_rcp, bit-identical codes).
+// path (uaq_codes_rcp, bit-identical codes).
 constexpr int kTileH = 8, kTileW = 16, kTileC = 64;
 
 template <typename TIn, int KS, int QMODE>
@@ -249,12 +253,13 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
       v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
       uint32_t lo = 0, hi = 0;
       if (QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized)) {
+        float cd[8];
+        uaq_codes_rcp<8>(v, d, inv, z, q.qmax, cd);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float cd = uaq_code_rcp(v[i], d[i], inv[i], z[i], q.qmax);
-          v[i] = q.emit_int ? __fsub_rn(cd, z[i]) : uaq_dequant(cd, d[i], z[i]);
-          if (i < 4) lo |= static_cast<uint32_t>(cd) << (8 * i);
-          else hi |= static_cast<uint32_t>(cd) << (8 * (i - 4));
+          v[i] = q.emit_int ? __fsub_rn(cd[i], z[i]) : uaq_dequant(cd[i], d[i], z[i]);
+          if (i < 4) lo |= static_cast<uint32_t>(cd[i]) << (8 * i);
+          else hi |= static_cast<uint32_t>(cd[i]) << (8 * (i - 4));
         }
       }
       *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + k0) = pack8(v);
