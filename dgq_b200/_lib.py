@@ -21,7 +21,7 @@ EPI_PLAIN, EPI_GEGLU, EPI_QKV = 0, 1, 2
 
 
 class QuantT(C.Structure):
-    _fields_ = [("delta", C.c_void_p), ("zp", C.c_void_p), ("mode", C.c_int), ("period", C.c_int),
+    _fields_ = [("delta", C.c_void_p), ("zp", C.c_void_p), ("inv_delta", C.c_void_p), ("mode", C.c_int), ("period", C.c_int),
                 ("qmax", C.c_float), ("emit_int", C.c_int)]
 
 

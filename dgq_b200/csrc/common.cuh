@@ -74,6 +74,60 @@ __device__ __forceinline__ void uaq_codes_rcp1(const float (&x)[N], float delta,
   for (int i = 0; i < N; ++i) code[i] = fminf(fmaxf(code[i] + zp, 0.0f), qmax);
 }
 
+// Lean form for the fused producers (no code output): value = delta * (code - zp), or the integer
+// (code - zp) when kEmitInt.  ~12 FP32 instructions per element; `inv` must be the correctly rounded
+// 1/delta.  No clamp before the magic-add rint: for |t| >= 2^22 the rounded value may be off by a few
+// units, which either trips the near-tie test (exact path) or saturates the [0, qmax] clamp anyway.
+template <bool kEmitInt, int N>
+__device__ __forceinline__ void uaq_lean(float (&v)[N], const float (&delta)[N], const float (&inv)[N],
+                                         const float (&zp)[N], float qmax) {
+  float r[N];
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float t = __fmul_rn(v[i], inv[i]);
+    r[i] = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+    near_tie |= fmaf(fabsf(t), -4.76837158e-7f, 0.5f - fabsf(__fsub_rn(t, r[i]))) <= 0.0f;
+  }
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = rintf(__fdiv_rn(v[i], delta[i]));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float q = __fsub_rn(fminf(fmaxf(__fadd_rn(r[i], zp[i]), 0.0f), qmax), zp[i]);
+    v[i] = kEmitInt ? q : __fmul_rn(delta[i], q);
+  }
+}
+// one (delta, 1/delta, zp) for all N values
+template <bool kEmitInt, int N>
+__device__ __forceinline__ void uaq_lean1(float (&v)[N], float delta, float inv, float zp, float qmax) {
+  float r[N];
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float t = __fmul_rn(v[i], inv);
+    r[i] = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+    near_tie |= fmaf(fabsf(t), -4.76837158e-7f, 0.5f - fabsf(__fsub_rn(t, r[i]))) <= 0.0f;
+  }
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = rintf(__fdiv_rn(v[i], delta));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float q = __fsub_rn(fminf(fmaxf(__fadd_rn(r[i], zp), 0.0f), qmax), zp);
+    v[i] = kEmitInt ? q : __fmul_rn(delta, q);
+  }
+}
+
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // erf-GELU (torch.nn.functional.gelu default), branch-free: erf by Abramowitz-Stegun 7.1.26

@@ -18,6 +18,7 @@ namespace dgq {
 struct QuantDev {
   const float* delta;
   const float* zp;
+  const float* inv;   // 1/delta (correctly rounded) or nullptr
   int mode;
   int period;
   float qmax;
@@ -25,7 +26,31 @@ struct QuantDev {
 };
 
 static QuantDev to_dev(const dgq_quant_t& q) {
-  return QuantDev{q.delta, q.zp, q.mode, q.period, q.qmax, q.emit_int};
+  return QuantDev{q.delta, q.zp, q.inv_delta, q.mode, q.period, q.qmax, q.emit_int};
+}
+
+// quantize 8 consecutive K positions k0..k0+7 of row `row` in place (no code output): the lean path
+// of every fused producer.  KWISE reads (delta, 1/delta, zp) vectors, SCALAR / ROWWISE one triple.
+__device__ __forceinline__ void quant8_lean(const QuantDev& q, float (&v)[8], int k0, int row) {
+  if (q.mode == DGQ_Q_NONE) return;
+  if (q.mode == DGQ_Q_KWISE) {
+    float d[8], z[8], inv[8];
+    ldg8(q.delta + k0, d);
+    ldg8(q.zp + k0, z);
+    if (q.inv != nullptr) {
+      ldg8(q.inv + k0, inv);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+    }
+    uaq_lean<false, 8>(v, d, inv, z, q.qmax);   // emit_int is not defined for K-wise scales
+  } else {
+    const int j = q.mode == DGQ_Q_ROWWISE ? row % q.period : 0;
+    const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j);
+    const float ii = q.inv != nullptr ? __ldg(q.inv + j) : __frcp_rn(dd);
+    if (q.emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
+    else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
+  }
 }
 
 __device__ __forceinline__ float to_f(float v) { return v; }
@@ -145,7 +170,7 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
 // path (uaq_codes_rcp, bit-identical codes).
 constexpr int kTileH = 8, kTileW = 16, kTileC = 64;
 
-template <typename TIn, int KS, int QMODE>
+template <typename TIn, int KS, int QMODE, bool kCodes>
 __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p, int tiles_x, int tiles_y) {
   constexpr int PH = kTileH + KS - 1, PW = kTileW + KS - 1;
   __shared__ __align__(16) float patch[PH * PW][kTileC];
@@ -216,19 +241,20 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
   const int cg = (tid & 7) * 8;
   const int ps = tid >> 3;  // 0..31
   const QuantDev& q = p.q;
+  const bool emit_int = q.emit_int != 0;
   for (int tap = 0; tap < KS * KS; ++tap) {
     const int dy = tap / KS, dx = tap % KS;
     const int k0 = tap * C + c0 + cg;
     float d[8], inv[8], z[8];
     if (QMODE == DGQ_Q_KWISE) {
-      const float4 d0 = __ldg(reinterpret_cast<const float4*>(q.delta + k0));
-      const float4 d1 = __ldg(reinterpret_cast<const float4*>(q.delta + k0 + 4));
-      const float4 z0 = __ldg(reinterpret_cast<const float4*>(q.zp + k0));
-      const float4 z1 = __ldg(reinterpret_cast<const float4*>(q.zp + k0 + 4));
-      d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
-      z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
+      ldg8(q.delta + k0, d);
+      ldg8(q.zp + k0, z);
+      if (q.inv != nullptr) {
+        ldg8(q.inv + k0, inv);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+        for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+      }
     } else if (QMODE == DGQ_Q_SCALAR) {
       const float dd = __ldg(q.delta), zz = __ldg(q.zp), ii = __frcp_rn(dd);
 #pragma unroll
@@ -241,30 +267,45 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
       if (oy >= p.ho || ox >= p.wo) continue;
       const int pp = (pl / kTileW + dy) * PW + (pl % kTileW + dx);
       const int m = (b * p.ho + oy) * p.wo + ox;
-      if (QMODE == DGQ_Q_ROWWISE) {
-        const int j = m % q.period;
-        const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j), ii = __frcp_rn(dd);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; inv[i] = ii; }
-      }
       float v[8];
       const float4 a0 = *reinterpret_cast<const float4*>(&patch[pp][cg]);
       const float4 a1 = *reinterpret_cast<const float4*>(&patch[pp][cg + 4]);
       v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-      uint32_t lo = 0, hi = 0;
-      if (QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized)) {
-        float cd[8];
-        uaq_codes_rcp<8>(v, d, inv, z, q.qmax, cd);
+      const bool quantize = QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized);
+      if (kCodes) {
+        if (QMODE == DGQ_Q_ROWWISE) {
+          const int j = m % q.period;
+          const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j), ii = __frcp_rn(dd);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v[i] = q.emit_int ? __fsub_rn(cd[i], z[i]) : uaq_dequant(cd[i], d[i], z[i]);
-          if (i < 4) lo |= static_cast<uint32_t>(cd[i]) << (8 * i);
-          else hi |= static_cast<uint32_t>(cd[i]) << (8 * (i - 4));
+          for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; inv[i] = ii; }
+        }
+        uint32_t lo = 0, hi = 0;
+        if (quantize) {
+          float cd[8];
+          uaq_codes_rcp<8>(v, d, inv, z, q.qmax, cd);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] = emit_int ? __fsub_rn(cd[i], z[i]) : uaq_dequant(cd[i], d[i], z[i]);
+            if (i < 4) lo |= static_cast<uint32_t>(cd[i]) << (8 * i);
+            else hi |= static_cast<uint32_t>(cd[i]) << (8 * (i - 4));
+          }
+        }
+        *reinterpret_cast<uint2*>(p.codes + static_cast<size_t>(m) * (KS * KS * C) + k0) = make_uint2(lo, hi);
+      } else if (quantize) {
+        if (QMODE == DGQ_Q_KWISE) {
+          uaq_lean<false, 8>(v, d, inv, z, q.qmax);
+        } else {
+          float dd = d[0], zz = z[0], ii = inv[0];
+          if (QMODE == DGQ_Q_ROWWISE) {
+            const int j = m % q.period;
+            dd = __ldg(q.delta + j); zz = __ldg(q.zp + j);
+            ii = q.inv != nullptr ? __ldg(q.inv + j) : __frcp_rn(dd);
+          }
+          if (emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
+          else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
         }
       }
       *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + k0) = pack8(v);
-      if (p.codes != nullptr)
-        *reinterpret_cast<uint2*>(p.codes + static_cast<size_t>(m) * (KS * KS * C) + k0) = make_uint2(lo, hi);
     }
   }
 }
@@ -273,11 +314,20 @@ template <typename TIn, int KS>
 static void launch_conv_producer(const ProducerDev& p, cudaStream_t s) {
   const int tiles_x = (p.wo + kTileW - 1) / kTileW, tiles_y = (p.ho + kTileH - 1) / kTileH;
   const int grid = p.batch * tiles_y * tiles_x * ((p.c0 + p.c1) / kTileC);
+  if (p.codes != nullptr) {   // verification path: also emits the integer codes
+    switch (p.q.mode) {
+      case DGQ_Q_KWISE: conv_producer_kernel<TIn, KS, DGQ_Q_KWISE, true><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+      case DGQ_Q_ROWWISE: conv_producer_kernel<TIn, KS, DGQ_Q_ROWWISE, true><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+      case DGQ_Q_SCALAR: conv_producer_kernel<TIn, KS, DGQ_Q_SCALAR, true><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+      default: conv_producer_kernel<TIn, KS, DGQ_Q_NONE, true><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    }
+    return;
+  }
   switch (p.q.mode) {
-    case DGQ_Q_KWISE: conv_producer_kernel<TIn, KS, DGQ_Q_KWISE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
-    case DGQ_Q_ROWWISE: conv_producer_kernel<TIn, KS, DGQ_Q_ROWWISE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
-    case DGQ_Q_SCALAR: conv_producer_kernel<TIn, KS, DGQ_Q_SCALAR><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
-    default: conv_producer_kernel<TIn, KS, DGQ_Q_NONE><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    case DGQ_Q_KWISE: conv_producer_kernel<TIn, KS, DGQ_Q_KWISE, false><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    case DGQ_Q_ROWWISE: conv_producer_kernel<TIn, KS, DGQ_Q_ROWWISE, false><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    case DGQ_Q_SCALAR: conv_producer_kernel<TIn, KS, DGQ_Q_SCALAR, false><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
+    default: conv_producer_kernel<TIn, KS, DGQ_Q_NONE, false><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y); break;
   }
 }
 
@@ -403,17 +453,33 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
       }
     }
   }
+#pragma unroll 1
   for (int o = 0; o < rq.n_out; ++o) {
+    const QuantDev q = rq.q[o];
+    __half* orow = rq.out[o] + static_cast<size_t>(warp) * c;
+    if (rq.codes[o] == nullptr) {
 #pragma unroll
-    for (int j = 0; j < kMaxVecPerLane; ++j) {
-      const int cv = lane + j * 32;
-      if (cv < cvec) {
-        float t[8];
+      for (int j = 0; j < kMaxVecPerLane; ++j) {
+        const int cv = lane + j * 32;
+        if (cv < cvec) {
+          float t[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = v[j][i];
-        uint8_t* cd = rq.codes[o] != nullptr ? rq.codes[o] + static_cast<size_t>(warp) * c + (cv << 3) : nullptr;
-        quant8(rq.q[o], t, cv << 3, warp, cd);
-        *reinterpret_cast<uint4*>(rq.out[o] + static_cast<size_t>(warp) * c + (cv << 3)) = pack8(t);
+          for (int i = 0; i < 8; ++i) t[i] = v[j][i];
+          quant8_lean(q, t, cv << 3, warp);
+          *reinterpret_cast<uint4*>(orow + (cv << 3)) = pack8(t);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kMaxVecPerLane; ++j) {
+        const int cv = lane + j * 32;
+        if (cv < cvec) {
+          float t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[i] = v[j][i];
+          quant8(q, t, cv << 3, warp, rq.codes[o] + static_cast<size_t>(warp) * c + (cv << 3));
+          *reinterpret_cast<uint4*>(orow + (cv << 3)) = pack8(t);
+        }
       }
     }
   }
@@ -434,7 +500,7 @@ __global__ void __launch_bounds__(256) geglu_quant_kernel(const TIn* __restrict_
     load8(x + static_cast<size_t>(row) * 2 * f + f + k0, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = a[i] * gelu_erf_f(g[i]);
-    quant8(q, a, k0, row, nullptr);
+    quant8_lean(q, a, k0, row);
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * f + k0) = pack8(a);
   }
 }
@@ -657,7 +723,7 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
   rq.n_out = n_out;
   for (int i = 0; i < 3; ++i) {
     rq.out[i] = nullptr; rq.codes[i] = nullptr;
-    rq.q[i] = QuantDev{nullptr, nullptr, DGQ_Q_NONE, 1, 0.f, 0};
+    rq.q[i] = QuantDev{nullptr, nullptr, nullptr, DGQ_Q_NONE, 1, 0.f, 0};
   }
   for (int i = 0; i < n_out; ++i) {
     DGQ_CHECK_ARG(out[i] != nullptr && quant_ok(q[i]));

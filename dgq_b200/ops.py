@@ -58,9 +58,12 @@ class QParam:
     period: int = 1
     qmax: float = 255.0
     int_ok: bool = False   # |code - zp| <= 2048 for every entry: the integer operand is exact in fp16
+    inv: Optional[torch.Tensor] = None   # 1/delta (IEEE), for the quantizer's multiply fast path
 
     def struct(self, emit_int: bool = False) -> L.QuantT:
-        return L.QuantT(_p(self.delta), _p(self.zp), self.mode, self.period, self.qmax, int(emit_int))
+        if self.inv is None and self.delta is not None:
+            self.inv = torch.reciprocal(self.delta)
+        return L.QuantT(_p(self.delta), _p(self.zp), _p(self.inv), self.mode, self.period, self.qmax, int(emit_int))
 
     @property
     def exact(self) -> bool:
@@ -81,7 +84,8 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     d, z = _f32(delta, device), _f32(zp, device)
     int_ok = bool((z.abs().max() + qmax <= 2048).item())
     if d.dim() == 0 or d.numel() == 1 and d.dim() <= 1:
-        return QParam(Q_SCALAR, d.reshape(1), z.reshape(1).expand(1).contiguous(), 1, qmax, int_ok)
+        d1 = d.reshape(1)
+        return QParam(Q_SCALAR, d1, z.reshape(1).expand(1).contiguous(), 1, qmax, int_ok, torch.reciprocal(d1))
     if d.dim() == 3 and d.shape[0] == 1 and d.shape[1] == 1:      # (1,1,X): last axis
         mode = Q_ROWWISE if conv else Q_KWISE
     elif d.dim() == 3 and d.shape[0] == 1 and d.shape[2] == 1:    # (1,X,1): middle axis
@@ -91,7 +95,8 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     d, z = d.reshape(-1), z.reshape(-1).expand(d.numel())
     if kperm is not None and mode == Q_KWISE:
         d, z = d[kperm], z[kperm]
-    return QParam(mode, d.contiguous(), z.contiguous(), d.numel(), qmax, int_ok)
+    d = d.contiguous()
+    return QParam(mode, d, z.contiguous(), d.numel(), qmax, int_ok, torch.reciprocal(d))
 
 
 # ------------------------------------------------------------------------------------------

@@ -39,6 +39,10 @@ extern "C" {
 typedef struct {
   const float* delta; /* device, 1 or many entries depending on mode */
   const float* zp;
+  const float* inv_delta; /* optional: 1/delta, correctly rounded, same indexing as delta; NULL: the
+                             kernels compute it (the quantizer multiplies by it on its fast path and
+                             falls back to the IEEE division near rounding ties, so codes stay
+                             bit-identical to round(x/delta))                                       */
   int mode;     /* DGQ_Q_*            */
   int period;   /* DGQ_Q_ROWWISE only */
   float qmax;   /* 2^bits - 1         */
