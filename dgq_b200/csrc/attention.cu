@@ -16,25 +16,47 @@
 //   log2 map : code = clamp(rint(beta_i + log2(delta) - s*alpha), 0, qmax),  P' = 2^-code
 //   uniform  : code = clamp(rint(2^(s*alpha - beta_i - log2(delta))), 0, qmax), P' = code
 //
-// CTA = 128 query rows of one (batch, head); 192 threads:
-//   warp 0 TMA loader | warp 1 MMA issuer (one lane) | warps 2..5 softmax: one thread per row
+// PERSISTENT CTAs: a work item is one 128-row query tile of one (batch, head); CTA c runs items
+// c, c + grid, ... as ONE continuous pipeline -- the K/V ring, the double-buffered S and P tiles, a
+// double-buffered Q tile and a double-buffered O accumulator all carry over from item to item, so the
+// QK^T of the next item overlaps the softmax / PV / epilogue of the current one (cross-attention,
+// S = 77, is a single K tile per item: without this it is launch- and latency-bound).
+// 320 threads:
+//   warp 0 TMA loader | warp 1 MMA issuer (one lane) | warps 2..9 softmax: thread = (row, column half)
 //   (TMEM lane == row, so row reductions need no shuffles).
-// TMEM: S double-buffered (2 x 128 cols) + O (dp cols).  P' goes through smem in the UMMA
-// K-major 128B-swizzle layout, written by the softmax threads.
+// TMEM: S 2 x 128 columns + O 1-2 x dp columns.  P' goes through smem in the UMMA K-major
+// 128B-swizzle layout, written by the softmax threads.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace dgq {
 
-constexpr int kAttThreads = 320;          // warp 0 loader, warp 1 MMA, warps 2..9 softmax
-constexpr int kSoftmaxThreads = 256;
+// warp 0 loader, warp 1 MMA, then the softmax warps: 8 in pass 1 (thread = row x 64-column half; the pass
+// is MUFU-bound and two CTAs share an SM), 16 in pass 2 (thread = row x 32-column quarter; one CTA per
+// SM, and the ALU-only map needs 4 warps per scheduler to cover its issue latency)
+template <int PASS> struct AttCfg {
+  static constexpr int kSoftmaxWarps = PASS == 1 ? 8 : 16;
+  static constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
+  // pass 2: warp 2 loads V on its own ring, so a K tile is never queued behind a V tile that waits for
+  // a PV to retire (the K/V prefetch distance was what bounded the whole kernel); warp 3 idles so that
+  // softmax warp w keeps TMEM lane quarter w & 3
+  static constexpr int kFirstSoftmaxWarp = PASS == 1 ? 2 : 4;
+  static constexpr int kThreads = 32 * kFirstSoftmaxWarp + kSoftmaxThreads;
+  static constexpr int kSplit = kSoftmaxWarps / 4;     // column splits of the 128-wide score tile
+  static constexpr int kCh = 4 / kSplit;               // 32-column chunks per thread
+};
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 x 64] fp16 SW128 sub-tile
+constexpr int kMaxKvStages = 4;
 
 struct AttnDev {
   int b, heads, t, s, d, dp;
-  int nkv, kv_stages, q_tiles;
+  int nkv, q_tiles, items;
+  int nh;                       // 128-row query halves per work item (2: each K/V tile is loaded once for both)
+  int nq_buf, nk_buf, nv_buf, no_buf, pv_lag;
   float alpha;  // scale * log2(e)
   int map_mode, real_time, start_peak;
   const float* delta;
@@ -51,28 +73,37 @@ struct AttnDev {
   // quantizer of the consuming QuantLayer (to_out[0]) applied to O in the epilogue
   const float* oq_delta;
   const float* oq_zp;
+  const float* oq_inv;
   int oq_mode, oq_period, oq_emit_int;
   float oq_qmax;
 };
 
-// barrier indices
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11,
-       B_PFULL = 13, B_PEMPTY = 15, B_OFULL = 17, B_COUNT = 18 };
+// barrier indices (rings of up to 4)
+constexpr int kRing = 4;
+enum { B_QFULL = 0, B_QEMPTY = B_QFULL + kRing, B_KFULL = B_QEMPTY + kRing, B_KEMPTY = B_KFULL + kRing,
+       B_VFULL = B_KEMPTY + kRing, B_VEMPTY = B_VFULL + kRing, B_SFULL = B_VEMPTY + kRing, B_SEMPTY = B_SFULL + 2,
+       B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_OEMPTY = B_OFULL + 2,
+       B_COUNT = B_OEMPTY + 2 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_bar_sync() {  // the 8 softmax warps only
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+template <int kThreads> __device__ __forceinline__ void softmax_bar_sync() {  // the softmax warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // ---- pass 2, 32 scores of one row -> 32 fp16 operand values P' (packed in 16 regs)
 //   MODE LOG2   : P' = 2^-code, code = clamp(rint(gamma - s*alpha), 0, qcap)   (no MUFU at all)
 //   MODE UNIFORM: P' = code = min(rint(2^(s*alpha - gamma)), qmax)
 //   MODE NONE   : P' = 2^(s*alpha - gamma)
-template <int MODE, bool MASK, bool CODES>
+// Columns beyond the key length need no mask for LOG2 / UNIFORM: their P' is finite and the matching
+// V^T columns are zero (TMA out-of-bounds fill / zeroed padding).  MODE NONE masks (2^-gamma may overflow).
+template <int MODE, bool CODES>
 __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2)[16], float alpha, float gamma,
                                           float qcap, float qmax, int col0, int s_len, uint8_t* code_row) {
 #pragma unroll
@@ -90,9 +121,8 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
       } else if (MODE == DGQ_MAP_UNIFORM) {
         val = fminf(rintf(ex2_approx(fmaf(alpha, sc, -gamma))), qmax);
       } else {
-        val = ex2_approx(fmaf(alpha, sc, -gamma));
+        val = (col0 + i + e < s_len) ? ex2_approx(fmaf(alpha, sc, -gamma)) : 0.f;
       }
-      if (MASK) val = (col0 + i + e < s_len) ? val : 0.f;
       if (CODES) {
         if (col0 + i + e < s_len && MODE != DGQ_MAP_NONE) {
           const float cd = MODE == DGQ_MAP_LOG2 ? fminf(rintf(fmaxf(fmaf(-alpha, sc, gamma), 0.f)), qmax) : val;
@@ -107,36 +137,38 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
 }
 
 template <int PASS, int MODE, bool CODES>
-__global__ void __launch_bounds__(kAttThreads, PASS == 1 ? 2 : 1)
+__global__ void __launch_bounds__(AttCfg<PASS>::kThreads, PASS == 1 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnDev p) {
+  using Cfg = AttCfg<PASS>;
+  constexpr int kSoftmaxWarps = Cfg::kSoftmaxWarps, kSoftmaxThreads = Cfg::kSoftmaxThreads;
+  constexpr int kSplit = Cfg::kSplit, kCh = Cfg::kCh;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int dchunks = p.dp >> 6;
-  const uint32_t q_bytes = dchunks * kChunkBytes;          // Q tile / one K stage
+  const uint32_t q_bytes = dchunks * kChunkBytes;          // one Q tile / one K stage
   const uint32_t v_stage = 2 * p.dp * 128;                 // two [dp x 64] sub-tiles
+  const uint32_t nqb = p.nq_buf, nkb = p.nk_buf, nvb = p.nv_buf, nob = p.no_buf, nh = p.nh;
   uint8_t* s_q = smem;
-  uint8_t* s_k = s_q + q_bytes;
-  uint8_t* s_v = s_k + p.kv_stages * q_bytes;
-  uint8_t* s_p = s_v + (PASS == 2 ? p.kv_stages * v_stage : 0);
+  uint8_t* s_k = s_q + nqb * q_bytes;
+  uint8_t* s_v = s_k + nkb * q_bytes;
+  uint8_t* s_p = s_v + (PASS == 2 ? nvb * v_stage : 0);
   uint8_t* s_end = s_p + (PASS == 2 ? 2 * 2 * kChunkBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_end);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [192] v_hat row 0 (start-peak)
-  float* s_x = s_v0 + 192;                                 // [3][128] cross-half exchange
+  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [2][192] v_hat row 0 of the item's head (start-peak)
+  float* s_x = s_v0 + 2 * 192;                             // [3][128] cross-split exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x % p.q_tiles;
-  const int bh = blockIdx.x / p.q_tiles;
-  const int nst = p.kv_stages;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_q);
     prefetch_tmap(&tm_k);
     if (PASS == 2) prefetch_tmap(&tm_v);
     for (int i = 0; i < B_COUNT; ++i) {
-      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2);
-      mbar_init(&bars[i], all_sm ? 8 : 1);
+      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2) ||
+                          (i >= B_OEMPTY && i < B_OEMPTY + 2);
+      mbar_init(&bars[i], all_sm ? kSoftmaxWarps : 1);
     }
     fence_barrier_init();
   }
@@ -145,46 +177,67 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (PASS == 2 && p.start_peak && threadIdx.x >= 64) {
-    for (int dd = threadIdx.x - 64; dd < p.dp; dd += kSoftmaxThreads)
-      s_v0[dd] = __half2float(p.vt[(static_cast<size_t>(bh) * p.dp + dd) * p.sp]);
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;
+  const int q_groups = (p.q_tiles + static_cast<int>(nh) - 1) / static_cast<int>(nh);   // items per (batch, head)
 
+  // Sequence numbers shared by all roles (each role counts them itself):
+  //   it = item counter of this CTA;  g = K/V tile counter;  u = g * nh + h = score-tile step counter
+  //   S / P' buffer = u & 1;  Q tile number = it * nh + h;  O accumulator number = it * nh + h
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA loader
+    // ------------------------------------------------------------------ TMA loader: Q and K
     if (lane == 0) {
-      mbar_arrive_expect_tx(&bars[B_QFULL], q_bytes);
-      for (int c = 0; c < dchunks; ++c)
-        tma_load_3d(s_q + c * kChunkBytes, &tm_q, &bars[B_QFULL], c * 64, q_tile * kTileQ, bh);
-      for (int j = 0; j < p.nkv; ++j) {
-        const int slot = j % nst;
-        const uint32_t ph = (j / nst) & 1;
-        mbar_wait(&bars[B_KEMPTY + slot], ph ^ 1);
-        mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
-        for (int c = 0; c < dchunks; ++c)
-          tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], c * 64, j * kTileK, bh);
-        if (PASS == 2) {
-          mbar_wait(&bars[B_VEMPTY + slot], ph ^ 1);
+      uint32_t g = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int qg = item % q_groups, bh = item / q_groups;
+        for (uint32_t h = 0; h < nh; ++h) {
+          const uint32_t qn = it * nh + h, qb = qn % nqb;
+          mbar_wait(&bars[B_QEMPTY + qb], ((qn / nqb) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[B_QFULL + qb], q_bytes);
+          for (int c = 0; c < dchunks; ++c)
+            tma_load_3d(s_q + qb * q_bytes + c * kChunkBytes, &tm_q, &bars[B_QFULL + qb], c * 64,
+                        (qg * static_cast<int>(nh) + static_cast<int>(h)) * kTileQ, bh);
+        }
+        for (int j = 0; j < p.nkv; ++j, ++g) {
+          const uint32_t slot = g % nkb;
+          mbar_wait(&bars[B_KEMPTY + slot], ((g / nkb) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
+          for (int c = 0; c < dchunks; ++c)
+            tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], c * 64, j * kTileK, bh);
+        }
+      }
+    }
+  } else if (PASS == 2 && warp == 2) {
+    // ------------------------------------------------------------------ V loader (own ring, own thread)
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const int bh = item / q_groups;
+        for (int j = 0; j < p.nkv; ++j, ++g) {
+          const uint32_t slot = g % nvb;
+          mbar_wait(&bars[B_VEMPTY + slot], ((g / nvb) & 1) ^ 1);
           mbar_arrive_expect_tx(&bars[B_VFULL + slot], v_stage);
           for (int c = 0; c < 2; ++c)
             tma_load_3d(s_v + slot * v_stage + c * (p.dp * 128), &tm_v, &bars[B_VFULL + slot], j * kTileK + c * 64, 0, bh);
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (PASS == 2 && warp == 3) {
+    // ------------------------------------------------------------------ PV issuer (own thread: every
+    // mbarrier wait / commit costs the issuing thread ~100+ cycles of latency, so one thread issuing
+    // both QK^T and PV serialises ~12 such operations per 128 x 128 step and becomes the critical path)
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileK);
       const uint32_t idesc_o = umma_idesc_f16(kTileQ, p.dp);
-      auto issue_pv = [&](int i) {
-        const int slot = i % nst, pb = i & 1;
-        mbar_wait(&bars[B_VFULL + slot], (i / nst) & 1);
-        mbar_wait(&bars[B_PFULL + pb], (i >> 1) & 1);
+      // O[on] += P'(u) V(g):  u = score-tile step, g = its K/V tile, on = O accumulator number,
+      // first / last = first / last K tile of the item, lastq = last query half using V(g)
+      auto issue_pv = [&](uint32_t u, uint32_t g, uint32_t on, bool first, bool last, bool lastq) {
+        const uint32_t slot = g % nvb, pb = u & 1, ob = on % nob;
+        mbar_wait(&bars[B_VFULL + slot], (g / nvb) & 1);
+        mbar_wait(&bars[B_PFULL + pb], (u >> 1) & 1);
+        if (first) mbar_wait(&bars[B_OEMPTY + ob], ((on / nob) & 1) ^ 1);   // the epilogue drained this accumulator
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -192,208 +245,271 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const uint64_t db = umma_desc_sw128(smem_u32(s_v + slot * v_stage + c * (p.dp * 128)));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            tc_mma_f16(tmem_o, da + 2 * ks, db + 2 * ks, idesc_o, (i | c | ks) != 0 ? 1u : 0u);
+            tc_mma_f16(tmem_o + ob * p.dp, da + 2 * ks, db + 2 * ks, idesc_o, (!first || (c | ks) != 0) ? 1u : 0u);
         }
-        tc_commit(&bars[B_VEMPTY + slot]);
+        if (lastq) tc_commit(&bars[B_VEMPTY + slot]);
         tc_commit(&bars[B_PEMPTY + pb]);
+        if (last) tc_commit(&bars[B_OFULL + ob]);
       };
-      mbar_wait(&bars[B_QFULL], 0);
-      for (int j = 0; j < p.nkv; ++j) {
-        const int slot = j % nst, sb = j & 1;
-        mbar_wait(&bars[B_KFULL + slot], (j / nst) & 1);
-        mbar_wait(&bars[B_SEMPTY + sb], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < dchunks; ++c) {
-          const uint64_t da = umma_desc_sw128(smem_u32(s_q + c * kChunkBytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * q_bytes + c * kChunkBytes));
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (c | ks) != 0 ? 1u : 0u);
+      uint32_t u = 0, g = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        for (int j = 0; j < p.nkv; ++j, ++g) {
+          for (uint32_t h = 0; h < nh; ++h, ++u)
+            issue_pv(u, g, it * nh + h, j == 0, j == p.nkv - 1, h == nh - 1);
         }
-        tc_commit(&bars[B_KEMPTY + slot]);
-        tc_commit(&bars[B_SFULL + sb]);
-        if (PASS == 2 && j > 0) issue_pv(j - 1);
       }
-      if (PASS == 2) {
-        issue_pv(p.nkv - 1);
-        tc_commit(&bars[B_OFULL]);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ QK^T issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileK);
+      uint32_t u = 0, g = 0, it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        for (int j = 0; j < p.nkv; ++j, ++g) {
+          const uint32_t slot = g % nkb;
+          mbar_wait(&bars[B_KFULL + slot], (g / nkb) & 1);
+          for (uint32_t h = 0; h < nh; ++h, ++u) {
+            const uint32_t qn = it * nh + h, qb = qn % nqb, sb = u & 1;
+            if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
+            mbar_wait(&bars[B_SEMPTY + sb], ((u >> 1) & 1) ^ 1);
+            tc_fence_after();
+            for (int c = 0; c < dchunks; ++c) {
+              const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + c * kChunkBytes));
+              const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * q_bytes + c * kChunkBytes));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (c | ks) != 0 ? 1u : 0u);
+            }
+            tc_commit(&bars[B_SFULL + sb]);
+            if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this K tile
+            if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);         // last read of this Q tile
+          }
+        }
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps (2..9)
-    // warp -> TMEM lane quarter (warp & 3) and column half ((warp - 2) >> 2): one thread per
-    // (row, 64-column half) of the 128 x 128 score tile
+    // ------------------------------------------------------------------ softmax warps
+    // warp -> TMEM lane quarter (warp & 3) and column split: one thread per (row, 128 / kSplit columns)
+    // of each 128 x 128 score tile
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int row = quad * 32 + lane;           // row inside the tile == TMEM lane
-    const int tq = q_tile * kTileQ + row;       // query index
-    const bool row_ok = tq < p.t;
-    const size_t ridx = static_cast<size_t>(bh) * p.t + tq;
+    const int half = (warp - Cfg::kFirstSoftmaxWarp) >> 2;   // column split index, 0 .. kSplit - 1
+    const int col_lo = half * (128 / kSplit);     // first score column of this thread inside a tile
+    const int etid = threadIdx.x - 32 * Cfg::kFirstSoftmaxWarp;
+    const int row = quad * 32 + lane;             // row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const bool partial_last = (p.s % kTileK) != 0;
+    const uint32_t sp_base = smem_u32(s_p);
+    uint32_t u = 0, it = 0;
 
-    if (PASS == 1) {
-      float M = -INFINITY, Mx = -INFINITY, l = 0.f;
-      for (int j = 0; j < p.nkv; ++j) {
-        const int sb = j & 1;
-        mbar_wait(&bars[B_SFULL + sb], (j >> 1) & 1);
-        tc_fence_after();
-        const bool mask = partial_last && j == p.nkv - 1;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int qg = item % q_groups, bh = item / q_groups;
+      int tq[2];
+      bool row_ok[2];
+      size_t ridx[2];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 2 + cc;
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + c * 32, r);
-          tc_wait_ld();
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) * p.alpha;
-          if (mask) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (j * kTileK + c * 32 + i < p.s) ? x[i] : -INFINITY;
-          }
-          float cm = x[1];
-#pragma unroll
-          for (int i = 2; i < 32; ++i) cm = fmaxf(cm, x[i]);
-          const float cmx = cm;                 // excludes element 0 of this chunk
-          cm = fmaxf(cm, x[0]);
-          Mx = fmaxf(Mx, (j == 0 && c == 0) ? cmx : cm);
-          const float Mn = fmaxf(M, cm);
-          if (Mn > -INFINITY) {
-            float acc = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc += ex2_approx(x[i] - Mn);
-            l = l * ex2_approx(M - Mn) + acc;
-            M = Mn;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
+      for (int h = 0; h < 2; ++h) {
+        tq[h] = (qg * static_cast<int>(nh) + h) * kTileQ + row;   // query index
+        row_ok[h] = h < static_cast<int>(nh) && tq[h] < p.t;
+        ridx[h] = static_cast<size_t>(bh) * p.t + tq[h];
       }
-      // combine the two column halves of each row
-      if (half == 1) { s_x[row] = M; s_x[128 + row] = l; s_x[256 + row] = Mx; }
-      softmax_bar_sync();
-      if (half == 0) {
-        const float M1 = s_x[row], l1 = s_x[128 + row], Mx1 = s_x[256 + row];
-        const float Mn = fmaxf(M, M1);
-        if (Mn > -INFINITY) l = l * ex2_approx(M - Mn) + l1 * ex2_approx(M1 - Mn);
-        M = Mn;
-        Mx = fmaxf(Mx, Mx1);
-        float rp = 0.f;
-        if (row_ok) {
-          p.row_max[ridx] = M;
-          p.row_sum[ridx] = l;
-          rp = (p.start_peak ? ex2_approx(Mx - M) : 1.0f) / l;
-        }
-        for (int o = 16; o > 0; o >>= 1) rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, o));
-        if (lane == 0 && p.real_time) atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(rp));
-      }
-    } else {
-      // ---------------------------------------------------------------- pass 2
-      float delta = 1.0f;
-      if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
-      const float beta = row_ok ? (p.row_max[ridx] + log2f(p.row_sum[ridx])) : 0.f;
-      const float gamma = beta + (MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f);
-      const float qcap = fminf(p.qmax, 126.f);
-      float p0 = 0.f;                           // un-quantised start-peak probability of this row
-      uint8_t* code_row = CODES ? p.codes + ridx * p.s : nullptr;
-      for (int j = 0; j < p.nkv; ++j) {
-        const int sb = j & 1;
-        mbar_wait(&bars[B_SFULL + sb], (j >> 1) & 1);
-        mbar_wait(&bars[B_PEMPTY + sb], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const bool mask = (partial_last && j == p.nkv - 1) || (CODES && !row_ok);
-        uint8_t* sub = s_p + sb * 2 * kChunkBytes + half * kChunkBytes;   // this half's [128 x 64] sub-tile
+
+      if (PASS == 1) {
+        float M[2] = {-INFINITY, -INFINITY}, Mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+        for (int j = 0; j < p.nkv; ++j) {
+          const bool mask = partial_last && j == p.nkv - 1;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = half * 2 + cc;
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + c * 32, r);
-          tc_wait_ld();
-          uint32_t h2[16];
-          const int col0 = j * kTileK + c * 32;
-          if (mask) map_chunk<MODE, true, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, col0, row_ok ? p.s : 0, code_row);
-          else map_chunk<MODE, false, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, col0, p.s, code_row);
-          if (p.start_peak && j == 0 && c == 0) {
-            p0 = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0]), -beta));
-            h2[0] &= 0xFFFF0000u;               // column 0 leaves the MMA; added back in the epilogue
-          }
+          for (int h = 0; h < 2; ++h) {
+            if (h >= static_cast<int>(nh)) break;
+            const uint32_t sb = u & 1;
+            mbar_wait(&bars[B_SFULL + sb], (u >> 1) & 1);
+            ++u;
+            tc_fence_after();
+            uint32_t r[kCh][32];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            *reinterpret_cast<uint4*>(sub + sw128_offset(row, cc * 4 + v)) =
-                make_uint4(h2[4 * v], h2[4 * v + 1], h2[4 * v + 2], h2[4 * v + 3]);
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&bars[B_SEMPTY + sb]);
-          mbar_arrive(&bars[B_PFULL + sb]);
-        }
-      }
-      // ---- epilogue: O * out_scale (+ p0 * v0) -> out; the two halves split the dp columns
-      if (p.start_peak) {
-        if (half == 0) s_x[row] = p0;
-        softmax_bar_sync();
-        p0 = s_x[row];
-      }
-      mbar_wait(&bars[B_OFULL], 0);
-      tc_fence_after();
-      const float oscale = MODE == DGQ_MAP_NONE ? 1.0f : delta;
-      const int head = bh % p.heads, bb = bh / p.heads;
-      const size_t ooff = (static_cast<size_t>(bb) * p.t + tq) * p.ldo + head * p.d;
-      __half* orow = static_cast<__half*>(p.out) + ooff;
-      float* orow32 = static_cast<float*>(p.out) + ooff;
-      const int dhalf = p.dp >> 1;
-      for (int c = half * dhalf; c < (half + 1) * dhalf; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_o + lane_addr + c, r);
-        tc_wait_ld();
-        if (row_ok) {
+            for (int cc = 0; cc < kCh; ++cc) tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + col_lo + cc * 32, r[cc]);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);   // scores are in registers: free the S tile
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int d0 = c + v * 8;
-            if (d0 < p.d) {
-              float f[8];
+            for (int cc = 0; cc < kCh; ++cc) {
+              const int c = half * kCh + cc;
+              float x[32];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
-                if (p.start_peak) f[i] = fmaf(p0, s_v0[d0 + i], f[i]);
+              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[cc][i]) * p.alpha;
+              if (mask) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x[i] = (j * kTileK + c * 32 + i < p.s) ? x[i] : -INFINITY;
               }
-              if (p.oq_mode != DGQ_Q_NONE) {
-                float qd[8], qz[8];
-                if (p.oq_mode == DGQ_Q_KWISE) {
-                  const int k0 = head * p.d + d0;
-                  const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.oq_delta + k0));
-                  const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.oq_delta + k0 + 4));
-                  const float4 z0 = __ldg(reinterpret_cast<const float4*>(p.oq_zp + k0));
-                  const float4 z1 = __ldg(reinterpret_cast<const float4*>(p.oq_zp + k0 + 4));
-                  qd[0] = a0.x; qd[1] = a0.y; qd[2] = a0.z; qd[3] = a0.w; qd[4] = a1.x; qd[5] = a1.y; qd[6] = a1.z; qd[7] = a1.w;
-                  qz[0] = z0.x; qz[1] = z0.y; qz[2] = z0.z; qz[3] = z0.w; qz[4] = z1.x; qz[5] = z1.y; qz[6] = z1.z; qz[7] = z1.w;
-                } else {
-                  const int j = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>((static_cast<size_t>(bb) * p.t + tq) % p.oq_period) : 0;
-                  const float dd = __ldg(p.oq_delta + j), zz = __ldg(p.oq_zp + j);
+              float cm = x[1];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) { qd[i] = dd; qz[i] = zz; }
-                }
-                float qi[8], cd[8];
+              for (int i = 2; i < 32; ++i) cm = fmaxf(cm, x[i]);
+              const float cmx = cm;                 // excludes element 0 of this chunk
+              cm = fmaxf(cm, x[0]);
+              Mx[h] = fmaxf(Mx[h], (j == 0 && c == 0) ? cmx : cm);
+              const float Mn = fmaxf(M[h], cm);
+              if (Mn > -INFINITY) {
+                float acc = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) qi[i] = __frcp_rn(qd[i]);
-                uaq_codes_rcp<8>(f, qd, qi, qz, p.oq_qmax, cd);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  f[i] = p.oq_emit_int ? __fsub_rn(cd[i], qz[i]) : uaq_dequant(cd[i], qd[i], qz[i]);
-              }
-              if (p.out_is_f32) {
-                *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
+                for (int i = 0; i < 32; ++i) acc += ex2_approx(x[i] - Mn);
+                l[h] = l[h] * ex2_approx(M[h] - Mn) + acc;
+                M[h] = Mn;
               }
             }
           }
+        }
+        // combine the column splits of each row
+        static_assert(PASS != 1 || kSplit == 2, "pass 1 exchanges one partial per row");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h >= static_cast<int>(nh)) break;
+          if (half == 1) { s_x[row] = M[h]; s_x[128 + row] = l[h]; s_x[256 + row] = Mx[h]; }
+          softmax_bar_sync<kSoftmaxThreads>();
+          if (half == 0) {
+            const float M1 = s_x[row], l1 = s_x[128 + row], Mx1 = s_x[256 + row];
+            const float Mn = fmaxf(M[h], M1);
+            float ll = l[h];
+            if (Mn > -INFINITY) ll = ll * ex2_approx(M[h] - Mn) + l1 * ex2_approx(M1 - Mn);
+            const float Mxx = fmaxf(Mx[h], Mx1);
+            float rp = 0.f;
+            if (row_ok[h]) {
+              p.row_max[ridx[h]] = Mn;
+              p.row_sum[ridx[h]] = ll;
+              rp = (p.start_peak ? ex2_approx(Mxx - Mn) : 1.0f) / ll;
+            }
+            for (int o = 16; o > 0; o >>= 1) rp = fmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, o));
+            if (lane == 0 && p.real_time) atomicMax(reinterpret_cast<int*>(p.gmax), __float_as_int(rp));
+          }
+          softmax_bar_sync<kSoftmaxThreads>();      // s_x is rewritten next
+        }
+      } else {
+        // ---------------------------------------------------------------- pass 2
+        float delta = 1.0f;
+        if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
+        const float lg_delta = MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f;
+        const float qcap = fminf(p.qmax, 126.f);
+        float beta[2], p0[2] = {0.f, 0.f};        // p0: un-quantised start-peak probability of this row
+#pragma unroll
+        for (int h = 0; h < 2; ++h) beta[h] = row_ok[h] ? (p.row_max[ridx[h]] + log2f(p.row_sum[ridx[h]])) : 0.f;
+        float* v0 = s_v0 + (it & 1) * 192;
+        if (p.start_peak) {
+          for (int dd = etid; dd < p.dp; dd += kSoftmaxThreads)
+            v0[dd] = __half2float(p.vt[(static_cast<size_t>(bh) * p.dp + dd) * p.sp]);
+        }
+        for (int j = 0; j < p.nkv; ++j) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h >= static_cast<int>(nh)) break;
+            const uint32_t sb = u & 1, ph = (u >> 1) & 1;
+            ++u;
+            mbar_wait(&bars[B_SFULL + sb], ph);
+            tc_fence_after();
+            uint32_t r[kCh][32];
+#pragma unroll
+            for (int cc = 0; cc < kCh; ++cc) tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + col_lo + cc * 32, r[cc]);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);   // scores are in registers: free the S tile
+            const int s_len = (CODES && !row_ok[h]) ? 0 : p.s;
+            uint8_t* code_row = CODES ? p.codes + ridx[h] * p.s : nullptr;
+            const float gamma = beta[h] + lg_delta;
+            uint32_t h2[kCh][16];
+#pragma unroll
+            for (int cc = 0; cc < kCh; ++cc)
+              map_chunk<MODE, CODES>(r[cc], h2[cc], p.alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len,
+                                     code_row);
+            if (p.start_peak && j == 0 && half == 0) {
+              p0[h] = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0][0]), -beta[h]));
+              h2[0][0] &= 0xFFFF0000u;              // column 0 leaves the MMA; added back in the epilogue
+            }
+            mbar_wait(&bars[B_PEMPTY + sb], ph ^ 1);   // PV of step u - 2 has consumed this P' buffer
+            // P' tile = two [128 x 64] SW128 sub-tiles; score column col -> sub-tile col / 64, 16-byte chunk (col % 64) / 8
+            const uint32_t sub = sp_base + sb * 2 * kChunkBytes + (col_lo >> 6) * kChunkBytes;
+            const int ch0 = (col_lo & 63) >> 3;
+#pragma unroll
+            for (int cc = 0; cc < kCh; ++cc) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                st_shared_v4(sub + sw128_offset(row, ch0 + cc * 4 + v), h2[cc][4 * v], h2[cc][4 * v + 1], h2[cc][4 * v + 2],
+                             h2[cc][4 * v + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
+          }
+        }
+        // ---- epilogue: O * out_scale (+ p0 * v0) -> out; the column splits share the dp columns
+        const float oscale = MODE == DGQ_MAP_NONE ? 1.0f : delta;
+        const int head = bh % p.heads, bb = bh / p.heads;
+        const int dsplit = p.dp / kSplit;         // 16-column multiples: dp = 64 / 128 / 192, kSplit = 4
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h >= static_cast<int>(nh)) break;
+          float pp0 = p0[h];
+          if (p.start_peak) {
+            if (half == 0) s_x[row] = pp0;
+            softmax_bar_sync<kSoftmaxThreads>();
+            pp0 = s_x[row];
+          }
+          const uint32_t on = it * nh + h, ob = on % nob;
+          mbar_wait(&bars[B_OFULL + ob], (on / nob) & 1);
+          tc_fence_after();
+          const size_t orow_idx = static_cast<size_t>(bb) * p.t + tq[h];
+          const size_t ooff = orow_idx * p.ldo + head * p.d;
+          __half* orow = static_cast<__half*>(p.out) + ooff;
+          float* orow32 = static_cast<float*>(p.out) + ooff;
+          float rd = 1.f, rz = 0.f, ri = 1.f;       // row-indexed / scalar output quantizer
+          if (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE) {
+            const int jq = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>(orow_idx % p.oq_period) : 0;
+            rd = __ldg(p.oq_delta + jq); rz = __ldg(p.oq_zp + jq);
+            ri = p.oq_inv != nullptr ? __ldg(p.oq_inv + jq) : rcp_rn_slow(rd);
+          }
+          for (int c = half * dsplit; c < (half + 1) * dsplit; c += 16) {
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_o + ob * p.dp + lane_addr + c, r);
+            tc_wait_ld();
+            if (row_ok[h]) {
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const int d0 = c + v * 8;
+                if (d0 < p.d) {
+                  float f[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
+                    if (p.start_peak) f[i] = fmaf(pp0, v0[d0 + i], f[i]);
+                  }
+                  if (p.oq_mode == DGQ_Q_KWISE) {
+                    const int k0 = head * p.d + d0;
+                    float qd[8], qz[8], qi[8];
+                    ldg8(p.oq_delta + k0, qd);
+                    ldg8(p.oq_zp + k0, qz);
+                    if (p.oq_inv != nullptr) {
+                      ldg8(p.oq_inv + k0, qi);
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) qi[i] = rcp_rn_slow(qd[i]);
+                    }
+                    uaq_lean<false, 8>(f, qd, qi, qz, p.oq_qmax);
+                  } else if (p.oq_mode != DGQ_Q_NONE) {
+                    if (p.oq_emit_int) uaq_lean1<true, 8>(f, rd, ri, rz, p.oq_qmax);
+                    else uaq_lean1<false, 8>(f, rd, ri, rz, p.oq_qmax);
+                  }
+                  if (p.out_is_f32) {
+                    *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                  } else {
+                    *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_OEMPTY + ob]);
+          if (p.start_peak) softmax_bar_sync<kSoftmaxThreads>();   // s_x is rewritten next
         }
       }
     }
@@ -444,15 +560,25 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   AttnDev p;
   p.b = a->b; p.heads = a->heads; p.t = a->t; p.s = a->s; p.d = a->d; p.dp = a->dp;
   p.nkv = (a->s + kTileK - 1) / kTileK;
-  p.kv_stages = a->dp <= 64 ? 2 : 1;   // smem: dp 128/192 leave room for one K/V stage only
+  // Work item = nh 128-row query halves of one (batch, head): with nh = 2 every K/V tile is loaded once
+  // for both halves (the kernel is L2 -> smem bound otherwise).  TMEM (512 columns): S 2 x 128 + O 2 x dp,
+  // so dp = 192 runs nh = 1 with a single O accumulator.  smem (227 KB), in 16 KB units for dp = 64:
+  // Q 4 + K 3 + V 2 + P' 4; dp = 128: Q 2 + K 1 + V 1 (32 KB units) + P'; dp = 192: Q 1 + K 1 + V 1 (48 KB) + P'.
   p.q_tiles = (a->t + kTileQ - 1) / kTileQ;
+  p.nh = (a->dp <= 128 && p.q_tiles > 1) ? 2 : 1;
+  p.nq_buf = a->dp <= 64 ? 4 : (a->dp <= 128 ? 2 : 1);
+  p.nk_buf = a->dp <= 64 ? 3 : 1;
+  p.nv_buf = a->dp <= 64 ? 2 : 1;
+  p.no_buf = a->dp <= 128 ? 2 : 1;
+  p.pv_lag = (p.nv_buf >= 2 && p.nk_buf >= 2) ? 2 : 1;   // PV issued this many steps behind QK^T
+  p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
   p.alpha = a->scale * 1.4426950408889634f;
   p.map_mode = a->map_mode; p.real_time = a->real_time; p.start_peak = a->start_peak;
   p.delta = a->delta; p.qmax = a->qmax;
   p.row_max = a->row_max; p.row_sum = a->row_sum; p.gmax = a->gmax;
   p.vt = static_cast<const __half*>(a->vt); p.sp = a->sp;
   p.out = a->out; p.ldo = a->ldo; p.out_is_f32 = a->out_is_f32; p.codes = a->codes;
-  p.oq_delta = a->out_q.delta; p.oq_zp = a->out_q.zp; p.oq_mode = a->out_q.mode;
+  p.oq_delta = a->out_q.delta; p.oq_zp = a->out_q.zp; p.oq_inv = a->out_q.inv_delta; p.oq_mode = a->out_q.mode;
   p.oq_period = a->out_q.period > 0 ? a->out_q.period : 1; p.oq_emit_int = a->out_q.emit_int;
   p.oq_qmax = a->out_q.qmax;
 
@@ -466,9 +592,11 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   if (rc != 0) return rc;
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
-  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 192 * 4 + 3 * 128 * 4 + 64;
-  const uint32_t smem1 = q_bytes * (1 + p.kv_stages) + tail;
-  const uint32_t smem2 = q_bytes * (1 + p.kv_stages) + p.kv_stages * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
+  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 2 * 192 * 4 + 3 * 128 * 4 + 64;
+  AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring
+  if (p1.nq_buf > 2) p1.nq_buf = 2;
+  const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
+  const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
   KernelFn k1 = attention_kernel<1, 0, false>;
   KernelFn k2;
@@ -492,12 +620,14 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   }
   if (smem2 > 232448) return DGQ_ERR_INVALID_VALUE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = static_cast<int>(bh) * p.q_tiles;
+  // persistent CTAs: pass 1 fits two per SM (S only in TMEM), pass 2 one
+  const int grid1 = p.items < 2 * kNumSMs ? p.items : 2 * kNumSMs;
+  const int grid2 = p.items < kNumSMs ? p.items : kNumSMs;
   if (a->real_time) {
     cudaError_t e = cudaMemsetAsync(a->gmax, 0, sizeof(float), s);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  k1<<<grid, kAttThreads, smem1, s>>>(tq, tk, tv, p);
-  k2<<<grid, kAttThreads, smem2, s>>>(tq, tk, tv, p);
+  k1<<<grid1, AttCfg<1>::kThreads, smem1, s>>>(tq, tk, tv, p1);
+  k2<<<grid2, AttCfg<2>::kThreads, smem2, s>>>(tq, tk, tv, p);
   DGQ_RETURN_LAST_ERROR();
 }

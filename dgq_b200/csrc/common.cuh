@@ -74,6 +74,10 @@ __device__ __forceinline__ void uaq_codes_rcp1(const float (&x)[N], float delta,
   for (int i = 0; i < N; ++i) code[i] = fminf(fmaxf(code[i] + zp, 0.0f), qmax);
 }
 
+// rare paths kept out of line so the unrolled hot loops stay small (instruction cache)
+static __device__ __noinline__ float uaq_round_exact(float x, float delta) { return rintf(__fdiv_rn(x, delta)); }
+static __device__ __noinline__ float rcp_rn_slow(float d) { return __frcp_rn(d); }
+
 // Lean form for the fused producers (no code output): value = delta * (code - zp), or the integer
 // (code - zp) when kEmitInt.  ~12 FP32 instructions per element; `inv` must be the correctly rounded
 // 1/delta.  No clamp before the magic-add rint: for |t| >= 2^22 the rounded value may be off by a few
@@ -91,7 +95,7 @@ __device__ __forceinline__ void uaq_lean(float (&v)[N], const float (&delta)[N],
   }
   if (near_tie) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = rintf(__fdiv_rn(v[i], delta[i]));
+    for (int i = 0; i < N; ++i) r[i] = uaq_round_exact(v[i], delta[i]);
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -112,7 +116,7 @@ __device__ __forceinline__ void uaq_lean1(float (&v)[N], float delta, float inv,
   }
   if (near_tie) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) r[i] = rintf(__fdiv_rn(v[i], delta));
+    for (int i = 0; i < N; ++i) r[i] = uaq_round_exact(v[i], delta);
   }
 #pragma unroll
   for (int i = 0; i < N; ++i) {

@@ -41,13 +41,13 @@ __device__ __forceinline__ void quant8_lean(const QuantDev& q, float (&v)[8], in
       ldg8(q.inv + k0, inv);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+      for (int i = 0; i < 8; ++i) inv[i] = rcp_rn_slow(d[i]);
     }
     uaq_lean<false, 8>(v, d, inv, z, q.qmax);   // emit_int is not defined for K-wise scales
   } else {
     const int j = q.mode == DGQ_Q_ROWWISE ? row % q.period : 0;
     const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j);
-    const float ii = q.inv != nullptr ? __ldg(q.inv + j) : __frcp_rn(dd);
+    const float ii = q.inv != nullptr ? __ldg(q.inv + j) : rcp_rn_slow(dd);
     if (q.emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
     else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
   }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
         ldg8(q.inv + k0, inv);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) inv[i] = __frcp_rn(d[i]);
+        for (int i = 0; i < 8; ++i) inv[i] = rcp_rn_slow(d[i]);
       }
     } else if (QMODE == DGQ_Q_SCALAR) {
       const float dd = __ldg(q.delta), zz = __ldg(q.zp), ii = __frcp_rn(dd);
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
           if (QMODE == DGQ_Q_ROWWISE) {
             const int j = m % q.period;
             dd = __ldg(q.delta + j); zz = __ldg(q.zp + j);
-            ii = q.inv != nullptr ? __ldg(q.inv + j) : __frcp_rn(dd);
+            ii = q.inv != nullptr ? __ldg(q.inv + j) : rcp_rn_slow(dd);
           }
           if (emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
           else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
@@ -445,11 +445,11 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
     for (int j = 0; j < kMaxVecPerLane; ++j) {
       const int cv = lane + j * 32;
       if (cv < cvec) {
+        float ga[8], be[8];
+        ldg8(gamma + (cv << 3), ga);
+        ldg8(beta + (cv << 3), be);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int cc = (cv << 3) + i;
-          v[j][i] = (v[j][i] - mean) * rstd * __ldg(gamma + cc) + __ldg(beta + cc);
-        }
+        for (int i = 0; i < 8; ++i) v[j][i] = (v[j][i] - mean) * rstd * ga[i] + be[i];
       }
     }
   }
