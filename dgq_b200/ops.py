@@ -21,7 +21,7 @@ LAUNCHES = 0  # kernels launched through this module (some entry points launch t
 # dtype of activations BETWEEN kernels (GEMM results, residual stream).  fp32 keeps the inputs of
 # every quantizer identical to the reference's to ~1e-6; fp16 halves that traffic but moves ~1 % of
 # the values across a rounding boundary.  Tensor-core operands are fp16 either way.
-ACT_DTYPE = torch.float32
+ACT_DTYPE = torch.float16 if __import__("os").environ.get("DGQ_ACT_DTYPE", "fp32") == "fp16" else torch.float32
 
 
 def _is32(t: torch.Tensor) -> int:

@@ -118,6 +118,8 @@ def bench_gemm():
               (16384, 1280, 11520, "resid"), (65536, 5120, 640, "geglu"), (65536, 640, 640, "resid"),
               (65536, 640, 2560, "resid"), (65536, 640, 5760, "resid"), (16384, 1280, 1280, "qkv"),
               (1232, 1280, 2048, "qkv"), (262144, 320, 2880, "resid")]
+    if ONLY is not None and "gemm1" in ONLY:
+        shapes = shapes[1:2] + shapes[5:6]
     for m, n, k, kind in shapes:
         a = torch.randn(m, k, device=DEV).half()
         w = torch.randint(-8, 8, (n, k), device=DEV).half()
@@ -143,7 +145,7 @@ def bench_gemm():
 
 
 def main():
-    table = {"ln": bench_ln, "prod": bench_prod, "attn": bench_attn, "attn1": bench_attn, "gemm": bench_gemm}
+    table = {"ln": bench_ln, "prod": bench_prod, "attn": bench_attn, "attn1": bench_attn, "gemm": bench_gemm, "gemm1": bench_gemm}
     for name, fn in table.items():
         if ONLY is None or name in ONLY:
             fn()
