@@ -327,11 +327,75 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
       };
       const bool has_resid = kEpi == EPI_PLAIN && p.resid != nullptr;
+      const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
+      // ---- lean path of the fp32 residual stream (the hot case: every to_out / ff.net.2 / conv2 / proj_out
+      // layer): full tile, fp32 result (+ fp32 residual), bias / temb already folded into the staged tables.
+      // No per-element bounds or dtype branches; the next accumulator chunk is requested as soon as the
+      // current one is in registers.
+      if (kEpi == EPI_PLAIN && p.out == nullptr && (p.ep_is_f32 || (p.resid == nullptr && p.temb == nullptr)) &&
+          temb_row == nullptr && tile_row0 + kBM <= p.m && ncol0 + p.bn <= p.n && c_begin < c_end) {
+        const float* resid = static_cast<const float*>(p.resid);
+        const size_t row_a = static_cast<size_t>(warp_row0 + rl0);
+        auto ldres = [&](int c, float4 (&t)[8]) {
+          const float* b = resid + row_a * p.ld_resid + ncol0 + c * 32 + cq;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) t[rr] = __ldg(reinterpret_cast<const float4*>(b + static_cast<size_t>(rr) * 4 * p.ld_resid));
+        };
+        if (has_resid) ldres(c_begin, t_cur);
+        epi_bar_sync();                     // staged tables visible
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c_begin * 32, r);
+        const bool has_rs = p.row_scale != nullptr;
+        for (int c = c_begin; c < c_end; ++c) {
+          const int j0 = c * 32;
+          if (has_resid && c + 1 < c_end) ldres(c + 1, t_nxt);
+          tc_wait_ld();
+          float g[32];
+          if (has_rs) {
+            affine32(r, j0, g);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
+              const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
+              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]), sc.x, bi.x);
+              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]), sc.y, bi.y);
+              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]), sc.z, bi.z);
+              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]), sc.w, bi.w);
+            }
+          }
+          if (c + 1 < c_end) tmem_ld_32x32(t_row + j0 + 32, r);
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+          __syncwarp();
+          float* o = p.out_f32 + row_a * p.ldc + ncol0 + j0 + cq;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            float4 x = *reinterpret_cast<const float4*>(stg + (rr * 4 + rl0) * kStgLd + cq);
+            if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+            *reinterpret_cast<float4*>(o + static_cast<size_t>(rr) * 4 * p.ldc) = x;
+          }
+          __syncwarp();
+          if (has_resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
       epi_bar_sync();                       // staged tables visible
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
       for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         const int j0 = c * kUnit;           // first accumulator column of this iteration inside the tile
@@ -544,6 +608,12 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   GemmDev p;
   p.m = a->m; p.n = a->n; p.k = a->k;
   p.bn = pick_bn(a->n, a->epi == DGQ_EPI_GEGLU ? 64 : 32);
+  static int force_bn = -1;     // DGQ_GEMM_BN pins the N tile (benchmarking)
+  if (force_bn < 0) {
+    const char* env = getenv("DGQ_GEMM_BN");
+    force_bn = env != nullptr ? atoi(env) : 0;
+  }
+  if (force_bn > 0 && force_bn <= kMaxBN && force_bn % (a->epi == DGQ_EPI_GEGLU ? 64 : 32) == 0) p.bn = force_bn;
   p.n_tiles = (a->n + p.bn - 1) / p.bn;
   // CTA pairs (256-row tiles) once there is enough work to fill the 74 pairs; small problems keep
   // 128-row tiles on single CTAs so more SMs get a tile
