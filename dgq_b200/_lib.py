@@ -12,7 +12,7 @@ SYMBOLS = [
     "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight",
     "dgq_act_producer", "dgq_gn_stats", "dgq_ln_quant", "dgq_row_quant", "dgq_geglu_quant",
     "dgq_gemm_f16", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
-    "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add",
+    "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add", "dgq_sampler_step",
 ]
 
 Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE = 0, 1, 2, 3
@@ -54,6 +54,13 @@ class AttnT(C.Structure):
                 ("out_q", QuantT)]
 
 
+class SamplerStepT(C.Structure):
+    _fields_ = [("unet_out", C.c_void_p), ("n", C.c_int64), ("guidance", C.c_float), ("use_cfg", C.c_int),
+                ("eps_store", C.c_void_p), ("x", C.c_void_p), ("cx", C.c_float), ("c_eps", C.c_float),
+                ("hist", C.c_void_p * 4), ("c_hist", C.c_float * 4), ("noise", C.c_void_p), ("c_noise", C.c_float),
+                ("out", C.c_void_p), ("model_in", C.c_void_p), ("in_scale", C.c_float), ("dup", C.c_int)]
+
+
 _lib = None
 
 
@@ -85,6 +92,7 @@ def lib() -> C.CDLL:
             "dgq_nhwc_to_nchw": [vp, i, i, i, i, i, vp, vp],
             "dgq_silu": [vp, i, i64, vp, vp],
             "dgq_add": [vp, vp, i, i64, vp, vp],
+            "dgq_sampler_step": [C.POINTER(SamplerStepT), vp],
         }
         for name, args in sig.items():
             fn = getattr(l, name)

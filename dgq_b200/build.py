@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libdgq_b200.so")
-SOURCES = ["quantize.cu", "producer.cu", "gemm.cu", "attention.cu"]
+SOURCES = ["quantize.cu", "producer.cu", "gemm.cu", "attention.cu", "sampler.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
 

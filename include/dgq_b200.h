@@ -216,6 +216,33 @@ int dgq_silu(const void* x, int is_f32, int64_t n, void* out, void* stream);
 /* out = a + b; fp16 or fp32                                                                     */
 int dgq_add(const void* a, const void* b, int is_f32, int64_t n, void* out, void* stream);
 
+/* ---- sampler step (the caller of the path): CFG combine + scheduler update + next model
+ *      input in one pass.  Replaces pipeline_stable_diffusion.py:1022-1047 around PNDMScheduler.step_plms
+ *      (schedulers/scheduling_pndm.py:321-449) and EulerAncestralDiscreteScheduler.step / scale_model_input
+ *      (schedulers/scheduling_euler_ancestral_discrete.py:239-260,323-414), all of which are linear maps:
+ *        eps      = use_cfg ? u + guidance * (c - u) : unet_out        (u, c = the two halves of unet_out)
+ *        out      = cx * x + c_eps * eps + sum_k c_hist[k] * hist[k] + c_noise * noise
+ *        model_in = out * in_scale   (written twice, back to back, when dup: the CFG batch)
+ *      fp32, n = elements of ONE latent batch, multiple of 4.                                          */
+typedef struct {
+  const float* unet_out; /* [use_cfg ? 2n : n] */
+  int64_t n;
+  float guidance;
+  int use_cfg;
+  float* eps_store;      /* optional [n]: eps is kept here (the multistep history) */
+  const float* x;        /* [n] */
+  float cx, c_eps;
+  const float* hist[4];  /* earlier eps, NULL = unused */
+  float c_hist[4];
+  const float* noise;    /* [n], read only when c_noise != 0 */
+  float c_noise;
+  float* out;            /* [n] */
+  float* model_in;       /* optional [dup ? 2n : n] */
+  float in_scale;
+  int dup;
+} dgq_sampler_step_t;
+int dgq_sampler_step(const dgq_sampler_step_t* host_args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,14 +41,15 @@ def test_ctypes_structs_match_header_layout():
             decl = decl.strip()
             if not decl:
                 continue
-            parts = decl.replace("*", " ").split(",")
+            parts = re.sub(r"\[\d+\]", "", decl).replace("*", " ").split(",")
             first = parts[0].split()
             names.append(first[-1])
             names += [p.strip().split()[-1] for p in parts[1:]]
         return names
 
     for cname, ct in (("dgq_quant_t", _lib.QuantT), ("dgq_producer_t", _lib.ProducerT),
-                      ("dgq_gemm_t", _lib.GemmT), ("dgq_attn_t", _lib.AttnT)):
+                      ("dgq_gemm_t", _lib.GemmT), ("dgq_attn_t", _lib.AttnT),
+                      ("dgq_sampler_step_t", _lib.SamplerStepT)):
         assert c_fields(cname) == [f[0] for f in ct._fields_], cname
 
 
