@@ -90,8 +90,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-template <int kThreads> __device__ __forceinline__ void softmax_bar_sync() {  // the softmax warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+template <int kThreads> __device__ __forceinline__ void softmax_bar_sync(int id = 1) {  // the softmax warps only
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -136,13 +136,19 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
   }
 }
 
-template <int PASS, int MODE, bool CODES>
+// PP ("ping-pong", pass 2 with two query halves per item): softmax warps 0..7 own query half 0 (S / P' buffer 0,
+// O accumulator 0), warps 8..15 own half 1; thread = (row, 64-column half of the score tile).  The two groups
+// run half a step apart, so one group's TMEM-load / proxy-fence / barrier latencies and its whole O epilogue
+// are covered by the other group's ALU work (with all 16 warps in lock-step on one tile they were not:
+// 45 % issue utilisation, ncu profiles/r1e_attention.txt).
+template <int PASS, int MODE, bool CODES, bool PP>
 __global__ void __launch_bounds__(AttCfg<PASS>::kThreads, PASS == 1 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnDev p) {
   using Cfg = AttCfg<PASS>;
   constexpr int kSoftmaxWarps = Cfg::kSoftmaxWarps, kSoftmaxThreads = Cfg::kSoftmaxThreads;
-  constexpr int kSplit = Cfg::kSplit, kCh = Cfg::kCh;
+  constexpr int kSplit = PP ? 2 : Cfg::kSplit, kCh = PP ? 2 : Cfg::kCh;
+  constexpr int kGroupThreads = PP ? kSoftmaxThreads / 2 : kSoftmaxThreads;   // threads sharing one score tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int dchunks = p.dp >> 6;
@@ -156,8 +162,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* s_end = s_p + (PASS == 2 ? 2 * 2 * kChunkBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_end);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [2][192] v_hat row 0 of the item's head (start-peak)
-  float* s_x = s_v0 + 2 * 192;                             // [3][128] cross-split exchange
+  float* s_v0 = reinterpret_cast<float*>(tmem_slot + 2);   // [2 groups][2][192] v_hat row 0 of the item's head (start-peak)
+  float* s_x = s_v0 + 4 * 192;                             // [3][128] cross-split exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -168,7 +174,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int i = 0; i < B_COUNT; ++i) {
       const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2) ||
                           (i >= B_OEMPTY && i < B_OEMPTY + 2);
-      mbar_init(&bars[i], all_sm ? kSoftmaxWarps : 1);
+      mbar_init(&bars[i], all_sm ? (PP ? kSoftmaxWarps / 2 : kSoftmaxWarps) : 1);
     }
     fence_barrier_init();
   }
@@ -292,9 +298,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // warp -> TMEM lane quarter (warp & 3) and column split: one thread per (row, 128 / kSplit columns)
     // of each 128 x 128 score tile
     const int quad = warp & 3;
-    const int half = (warp - Cfg::kFirstSoftmaxWarp) >> 2;   // column split index, 0 .. kSplit - 1
+    const int grp = PP ? (warp - Cfg::kFirstSoftmaxWarp) >> 3 : 0;          // PP: the query half this warp owns
+    const int half = ((warp - Cfg::kFirstSoftmaxWarp) >> 2) & (kSplit - 1);   // column split index, 0 .. kSplit - 1
     const int col_lo = half * (128 / kSplit);     // first score column of this thread inside a tile
-    const int etid = threadIdx.x - 32 * Cfg::kFirstSoftmaxWarp;
+    const int etid = (threadIdx.x - 32 * Cfg::kFirstSoftmaxWarp) & (kGroupThreads - 1);   // index inside the group
     const int row = quad * 32 + lane;             // row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const bool partial_last = (p.s % kTileK) != 0;

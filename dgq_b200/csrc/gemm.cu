@@ -26,12 +26,20 @@ namespace dgq {
 constexpr int kBM = 128;           // rows of A per CTA
 constexpr int kBK = 64;
 constexpr int kMaxBN = 256;
-constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 for the plain epilogue (2 column splits per TMEM
+// lane quarter), 16 for the fused GEGLU / QKV epilogues (4 splits) -- those run ~40 dependent ALU
+// instructions per result, so with 2 warps per scheduler they, not the MMAs, bounded the tile time
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
-constexpr int kStgLd = 36;                         // padded row stride (floats) of the epilogue transpose buffer
+constexpr int kStgLd = 36;                         // padded row stride (floats) of the fp32 epilogue transpose buffer
 constexpr int kEpiTab = 5;                         // per-column tables staged per tile
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
+template <int kEpi> struct EpiCfg {
+  static constexpr int kWarps = kEpi == EPI_PLAIN ? 8 : 16;
+  static constexpr int kThreads = 64 + 32 * kWarps;
+  static constexpr int kSplit = kWarps / 4;        // column splits of a tile (one per warp of a lane quarter)
+  // per-warp transpose buffer: [32 rows][36] fp32 (plain), [32 rows][32] fp16 with a 16-byte XOR swizzle (fused)
+  static constexpr uint32_t kStgBytes = kEpi == EPI_PLAIN ? 32 * kStgLd * 4 : 32 * 32 * 2;
+};
 
 struct EpiQuant {   // quantizer applied by the fused epilogues (the NEXT op's activation quantizer)
   const float* delta;
@@ -41,13 +49,13 @@ struct EpiQuant {   // quantizer applied by the fused epilogues (the NEXT op's a
   int emit_int;
 };
 
-template <int kCtas> struct GemmCfg {
+template <int kCtas, int kEpi> struct GemmCfg {
   static constexpr int kStages = kCtas == 1 ? 3 : 5;
   static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // [2 buffers][scale | bias | q.delta | 1/q.delta | q.zp][256] fp32 + one [32 rows][36] fp32 transpose
   // buffer per epilogue warp
-  static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + kEpiWarps * 32 * kStgLd * 4;
+  static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + EpiCfg<kEpi>::kWarps * EpiCfg<kEpi>::kStgBytes;
   static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -71,8 +79,8 @@ struct GemmDev {
   int heads, d, dp, tokens, tp, transpose, skip_first;
 };
 
-__device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
 }
 
 // kCtas == 1: one CTA per 128 x bn tile.  kCtas == 2: a CTA pair (cluster of 2, cta_group::2) per
@@ -80,11 +88,13 @@ __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
 // MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
 // L2->smem bytes of the single-CTA tile.
 template <int kCtas, int kEpi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<kEpi>::kThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
-  using Cfg = GemmCfg<kCtas>;
+  using Cfg = GemmCfg<kCtas, kEpi>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = EpiCfg<kEpi>::kWarps;
+  constexpr int kSplit = EpiCfg<kEpi>::kSplit;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -190,15 +200,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     //              yields 32 features x1 * gelu(gate), quantised for ff.net.2, stored as its fp16 operand.
     //   EPI_QKV  : quantise with aqtizer_q/k/v and store head-split ([b,h,t,dp] or V^T [b,h,dp,tp]).
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int split = (warp - 2) >> 2;
     const int etid = threadIdx.x - 64;
     constexpr int kUnit = kEpi == EPI_GEGLU ? 64 : 32;   // accumulator columns consumed per iteration
     const int nch = p.bn / kUnit;
-    const int c_begin = half == 0 ? 0 : (nch + 1) / 2;
-    const int c_end = half == 0 ? (nch + 1) / 2 : nch;
+    const int c_begin = (nch * split + kSplit - 1) / kSplit;
+    const int c_end = (nch * (split + 1) + kSplit - 1) / kSplit;
     const size_t esz = p.ep_is_f32 ? 4 : 2;
     const bool temb_tile = p.temb != nullptr && (p.rows_per_batch % (kBM * kCtas)) == 0;
-    float* stg = s_epi + 2 * kEpiTab * kMaxBN + (warp - 2) * (32 * kStgLd);
+    float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_epi + 2 * kEpiTab * kMaxBN) +
+                                          (warp - 2) * EpiCfg<kEpi>::kStgBytes);
     const int rl0 = lane >> 3;          // row (0..3) inside a group of 4 rows
     const int cq = (lane & 7) * 4;      // first of this lane's 4 columns inside the chunk
     const EpiQuant& q2 = p.q2;
@@ -306,6 +317,142 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
         }
       };
+      if constexpr (kEpi != EPI_PLAIN) {
+        // ---- fused epilogues (16 warps: thread = one row x a quarter of the tile's columns).  A unit of 32
+        // results is produced in two batches of 16 (register budget: 112 per thread at 576 threads), packed to
+        // fp16, transposed through a swizzled 2 KB per-warp buffer and stored as 64-byte row segments.
+        auto affine16 = [&](const uint32_t (&r)[16], int j0, float (&g)[16]) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
+            const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
+            g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
+            g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
+            g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
+            g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+          }
+        };
+        auto fused_quant16 = [&](float (&g)[16], int slot0) {
+          if (!q_on || q_skip) return;
+          const bool rw = q2.mode == DGQ_Q_ROWWISE;
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            float x[8], dd[8], ii[8], zz[8], cd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = g[v * 8 + i];
+            if (rw) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { dd[i] = qd_row; ii[i] = qi_row; zz[i] = qz_row; }
+            } else {
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4) {
+                const float4 a = *reinterpret_cast<const float4*>(s_qd + slot0 + v * 8 + h4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(s_qi + slot0 + v * 8 + h4 * 4);
+                const float4 c = *reinterpret_cast<const float4*>(s_qz + slot0 + v * 8 + h4 * 4);
+                dd[h4 * 4] = a.x; dd[h4 * 4 + 1] = a.y; dd[h4 * 4 + 2] = a.z; dd[h4 * 4 + 3] = a.w;
+                ii[h4 * 4] = b.x; ii[h4 * 4 + 1] = b.y; ii[h4 * 4 + 2] = b.z; ii[h4 * 4 + 3] = b.w;
+                zz[h4 * 4] = c.x; zz[h4 * 4 + 1] = c.y; zz[h4 * 4 + 2] = c.z; zz[h4 * 4 + 3] = c.w;
+              }
+            }
+            uaq_codes_rcp<8>(x, dd, ii, zz, q2.qmax, cd);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              g[v * 8 + i] = q2.emit_int ? __fsub_rn(cd[i], zz[i]) : uaq_dequant(cd[i], dd[i], zz[i]);
+          }
+        };
+        const uint32_t t_acc = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
+        uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
+        const bool scatter_t = kEpi == EPI_QKV && p.transpose;
+        epi_bar_sync<32 * kEpiWarps>();     // staged tables visible
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        for (int c = c_begin; c < c_end; ++c) {
+          const int j0 = c * kUnit;         // first accumulator column of this unit inside the tile
+          uint32_t hp[16];                  // 32 results of this thread's row, fp16 pairs
+#pragma unroll
+          for (int sb = 0; sb < 2; ++sb) {
+            float g[16];
+            uint32_t r1[16];
+            tmem_ld_32x16(t_acc + j0 + sb * 16, r1);
+            if (kEpi == EPI_GEGLU) {
+              uint32_t r2[16];
+              tmem_ld_32x16(t_acc + j0 + 32 + sb * 16, r2);
+              tc_wait_ld();
+              float x2[16];
+              affine16(r1, j0 + sb * 16, g);
+              affine16(r2, j0 + 32 + sb * 16, x2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] *= gelu_erf_f(x2[i]);
+              fused_quant16(g, c * 32 + sb * 16);
+            } else {
+              tc_wait_ld();
+              affine16(r1, j0 + sb * 16, g);
+              fused_quant16(g, j0 + sb * 16);
+            }
+            if (scatter_t) {
+              // V^T [b, heads, dp, tp]: for a fixed column the 32 lanes hold 32 consecutive tokens
+              if (row_ok) {
+                int n = ncol0 + j0 + sb * 16;
+                int hh = n / p.d, dd = n - hh * p.d;
+                __half* base = p.out + (static_cast<size_t>(bat) * p.heads) * p.dp * p.tp + tok;
+#pragma unroll
+                for (int i = 0; i < 16; ++i, ++n) {
+                  if (n < p.n) base[(static_cast<size_t>(hh) * p.dp + dd) * p.tp] = __float2half_rn(g[i]);
+                  if (++dd == p.d) { dd = 0; ++hh; }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const __half2 h = __floats2half2_rn(g[2 * i], g[2 * i + 1]);
+                hp[sb * 8 + i] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+            }
+          }
+          if (!scatter_t) {
+            // row `lane`, 16-byte chunk v -> slot v ^ ((lane >> 1) & 3): conflict-free for the row-wise writes
+            // and for the reads below (lane = (row & 3, 8-byte column group))
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              *reinterpret_cast<uint4*>(stg8 + lane * 64 + ((v ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
+            __syncwarp();
+            // result column of this lane's 4 values: GEGLU feature index, otherwise the GEMM column
+            const int n = kEpi == EPI_GEGLU ? n_blk * (p.bn >> 1) + c * 32 + cq : ncol0 + j0 + cq;
+            const int n_lim = kEpi == EPI_GEGLU ? (p.n >> 1) : p.n;
+            if (n < n_lim) {
+              int hh = 0, dd = 0;
+              if (kEpi == EPI_QKV) { hh = n / p.d; dd = n - hh * p.d; }
+              const int ch = (lane & 7) >> 1, sub = (lane & 1) * 8;
+#pragma unroll
+              for (int rr = 0; rr < 8; ++rr) {
+                const int rl = rr * 4 + rl0;
+                const int grow = warp_row0 + rl;
+                if (grow < p.m) {
+                  const uint2 x = *reinterpret_cast<const uint2*>(stg8 + rl * 64 + ((ch ^ ((rl >> 1) & 3)) << 4) + sub);
+                  size_t o;
+                  if (kEpi == EPI_QKV) {
+                    int gb = wbat, gt = wtok + rl;          // (batch, token) of row grow, without a division
+                    while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
+                    o = ((static_cast<size_t>(gb) * p.heads + hh) * p.tokens + gt) * p.dp + dd;
+                  } else {
+                    o = static_cast<size_t>(grow) * p.ldc + n;
+                  }
+                  *reinterpret_cast<uint2*>(p.out + o) = x;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float4 t_cur[8], t_nxt[8];
       auto load_resid = [&](int c, float4 (&t)[8]) {
         const int n = ncol0 + c * 32 + cq;
@@ -342,7 +489,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int rr = 0; rr < 8; ++rr) t[rr] = __ldg(reinterpret_cast<const float4*>(b + static_cast<size_t>(rr) * 4 * p.ld_resid));
         };
         if (has_resid) ldres(c_begin, t_cur);
-        epi_bar_sync();                     // staged tables visible
+        epi_bar_sync<32 * kEpiWarps>();                     // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         uint32_t r[32];
@@ -393,7 +540,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         continue;
       }
       if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
-      epi_bar_sync();                       // staged tables visible
+      epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       for (int c = c_begin; c < c_end; ++c) {
@@ -546,20 +693,21 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<kCtas>::kSmem);
+                                         GemmCfg<kCtas, kEpi>::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
+  constexpr int kGemmThreads = EpiCfg<kEpi>::kThreads;
   if (kCtas == 1) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_f16_kernel<kCtas, kEpi><<<grid, kGemmThreads, GemmCfg<kCtas>::kSmem, s>>>(ta, tb, p);
+    gemm_f16_kernel<kCtas, kEpi><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi>::kSmem, s>>>(ta, tb, p);
   } else {
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = GemmCfg<kCtas>::kSmem;
+    cfg.dynamicSmemBytes = GemmCfg<kCtas, kEpi>::kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -587,7 +735,7 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   DGQ_CHECK_ARG(a->epi >= DGQ_EPI_PLAIN && a->epi <= DGQ_EPI_QKV);
   if (a->epi != DGQ_EPI_PLAIN) {
     const dgq_quant_t& q = a->q2;
-    DGQ_CHECK_ARG(a->out != nullptr && a->resid == nullptr);
+    DGQ_CHECK_ARG(a->out != nullptr && a->resid == nullptr && a->temb == nullptr);
     DGQ_CHECK_ARG(q.mode >= DGQ_Q_NONE && q.mode <= DGQ_Q_ROWWISE);
     DGQ_CHECK_ARG(q.mode == DGQ_Q_NONE || (q.delta != nullptr && q.zp != nullptr));
     DGQ_CHECK_ARG(q.mode != DGQ_Q_ROWWISE || q.period > 0);
