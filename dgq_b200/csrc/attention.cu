@@ -106,6 +106,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <int MODE, bool CODES>
 __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2)[16], float alpha, float gamma,
                                           float qcap, float qmax, int col0, int s_len, uint8_t* code_row) {
+  const float q_inv = __frcp_rn(qcap);
+  const float a_sat = -alpha * q_inv, g_sat = gamma * q_inv;   // loop-invariant: hoisted by the compiler
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     float pv[2];
@@ -114,9 +116,12 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
       const float sc = __uint_as_float(r[i + e]);
       float val;
       if (MODE == DGQ_MAP_LOG2) {
-        // rint through the 1.5*2^23 magic add; 2^-code rebuilt from the exponent field
-        const float xq = fminf(fmaxf(fmaf(-alpha, sc, gamma), 0.f), qcap);
-        const uint32_t yb = __float_as_uint(xq + 12582912.0f);
+        // x / qcap = gamma / qcap - s * alpha / qcap, clamped to [0, 1] by the FMA's own .sat (the two FMNMX of
+        // an explicit clamp run on the half-rate ALU pipe, which bounded this loop); rint(x) through the
+        // 1.5 * 2^23 magic add of a second FMA; 2^-code rebuilt from the exponent field by one IMAD
+        float y;
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(sc), "f"(a_sat), "f"(g_sat));
+        const uint32_t yb = __float_as_uint(fmaf(y, qcap, 12582912.0f));
         val = __uint_as_float(yb * 0xFF800000u + 0x3F800000u);
       } else if (MODE == DGQ_MAP_UNIFORM) {
         val = fminf(rintf(ex2_approx(fmaf(alpha, sc, -gamma))), qmax);
@@ -320,6 +325,134 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         ridx[h] = static_cast<size_t>(bh) * p.t + tq[h];
       }
 
+      // O accumulator `ob`, columns [c_lo, c_hi) of this thread's row: O * out_scale (+ p0 * v0), the to_out quantizer, store
+      const int head = bh % p.heads, bb = bh / p.heads;
+      auto store_o = [&](int tqh, bool rok, float pp0, const float* v0, float oscale, uint32_t ob, int c_lo, int c_hi) {
+          const size_t orow_idx = static_cast<size_t>(bb) * p.t + tqh;
+          const size_t ooff = orow_idx * p.ldo + head * p.d;
+          __half* orow = static_cast<__half*>(p.out) + ooff;
+          float* orow32 = static_cast<float*>(p.out) + ooff;
+          float rd = 1.f, rz = 0.f, ri = 1.f;       // row-indexed / scalar output quantizer
+          if (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE) {
+            const int jq = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>(orow_idx % p.oq_period) : 0;
+            rd = __ldg(p.oq_delta + jq); rz = __ldg(p.oq_zp + jq);
+            ri = p.oq_inv != nullptr ? __ldg(p.oq_inv + jq) : rcp_rn_slow(rd);
+          }
+          for (int c = c_lo; c < c_hi; c += 16) {
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_o + ob * p.dp + lane_addr + c, r);
+            tc_wait_ld();
+            if (rok) {
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const int d0 = c + v * 8;
+                if (d0 < p.d) {
+                  float f[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
+                    if (p.start_peak) f[i] = fmaf(pp0, v0[d0 + i], f[i]);
+                  }
+                  if (p.oq_mode == DGQ_Q_KWISE) {
+                    const int k0 = head * p.d + d0;
+                    float qd[8], qz[8], qi[8];
+                    ldg8(p.oq_delta + k0, qd);
+                    ldg8(p.oq_zp + k0, qz);
+                    if (p.oq_inv != nullptr) {
+                      ldg8(p.oq_inv + k0, qi);
+                    } else {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) qi[i] = rcp_rn_slow(qd[i]);
+                    }
+                    uaq_lean<false, 8>(f, qd, qi, qz, p.oq_qmax);
+                  } else if (p.oq_mode != DGQ_Q_NONE) {
+                    if (p.oq_emit_int) uaq_lean1<true, 8>(f, rd, ri, rz, p.oq_qmax);
+                    else uaq_lean1<false, 8>(f, rd, ri, rz, p.oq_qmax);
+                  }
+                  if (p.out_is_f32) {
+                    *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
+                    *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                  } else {
+                    *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
+                  }
+                }
+              }
+            }
+          }
+      };
+      if constexpr (PASS == 2 && PP) {
+        // ---------------------------------------------------------------- pass 2, ping-pong groups (nh == 2):
+        // this warp's group owns query half `grp` of the item: S / P' buffer grp, O accumulator grp.
+        // u counts the K/V tiles of this CTA (= the phase of the group's buffers).
+        const int tqh = (qg * 2 + grp) * kTileQ + row;
+        const bool rok = tqh < p.t;
+        const size_t rix = static_cast<size_t>(bh) * p.t + tqh;
+        float delta = 1.0f;
+        if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
+        const float lg_delta = MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f;
+        const float qcap = fminf(p.qmax, 126.f);
+        const float beta = rok ? (p.row_max[rix] + log2f(p.row_sum[rix])) : 0.f;
+        const float gamma = beta + lg_delta;
+        float p0 = 0.f;                           // un-quantised start-peak probability of this row
+        float* v0 = s_v0 + (grp * 2 + (it & 1)) * 192;
+        if (p.start_peak) {
+          for (int dd = etid; dd < p.dp; dd += kGroupThreads)
+            v0[dd] = __half2float(p.vt[(static_cast<size_t>(bh) * p.dp + dd) * p.sp]);
+        }
+        const uint32_t sb = grp;
+        const int s_len = (CODES && !rok) ? 0 : p.s;
+        uint8_t* code_row = CODES ? p.codes + rix * p.s : nullptr;
+        // this thread's 64 score columns are one [128 x 64] SW128 sub-tile of the P' buffer
+        const uint32_t sub = sp_base + sb * 2 * kChunkBytes + half * kChunkBytes;
+        for (int j = 0; j < p.nkv; ++j, ++u) {
+          const uint32_t ph = u & 1;
+          mbar_wait(&bars[B_SFULL + sb], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + col_lo + cc * 32, r);
+            tc_wait_ld();
+            if (cc == 1) {                        // all of this thread's scores are in registers: free the S tile
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
+            }
+            uint32_t h2[16];
+            map_chunk<MODE, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len, code_row);
+            if (cc == 0) {
+              if (p.start_peak && j == 0 && half == 0) {
+                p0 = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0]), -beta));
+                h2[0] &= 0xFFFF0000u;             // column 0 leaves the MMA; added back in the epilogue
+              }
+              mbar_wait(&bars[B_PEMPTY + sb], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              st_shared_v4(sub + sw128_offset(row, cc * 4 + v), h2[4 * v], h2[4 * v + 1], h2[4 * v + 2], h2[4 * v + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
+        }
+        // ---- epilogue of this group's half; the other group keeps the tensor pipe busy meanwhile
+        float pp0 = p0;
+        if (p.start_peak) {
+          if (half == 0) s_x[grp * 128 + row] = pp0;
+          softmax_bar_sync<kGroupThreads>(1 + grp);
+          pp0 = s_x[grp * 128 + row];
+        }
+        const uint32_t ob = grp;                  // O accumulator number it * 2 + grp, two accumulators
+        mbar_wait(&bars[B_OFULL + ob], it & 1);
+        tc_fence_after();
+        const int dsplit = p.dp >> 1;
+        store_o(tqh, rok, pp0, v0, MODE == DGQ_MAP_NONE ? 1.0f : delta, ob, half * dsplit, (half + 1) * dsplit);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_OEMPTY + ob]);
+        if (p.start_peak) softmax_bar_sync<kGroupThreads>(1 + grp);   // s_x / v0 are rewritten next
+        continue;
+      }
       if (PASS == 1) {
         float M[2] = {-INFINITY, -INFINITY}, Mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
         for (int j = 0; j < p.nkv; ++j) {
@@ -341,9 +474,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
             for (int cc = 0; cc < kCh; ++cc) {
               const int c = half * kCh + cc;
+              // row max on the raw scores (alpha > 0), then ex2(s * alpha - M) as ONE FMA + MUFU per element
               float x[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[cc][i]) * p.alpha;
+              for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[cc][i]);
               if (mask) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) x[i] = (j * kTileK + c * 32 + i < p.s) ? x[i] : -INFINITY;
@@ -351,14 +485,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               float cm = x[1];
 #pragma unroll
               for (int i = 2; i < 32; ++i) cm = fmaxf(cm, x[i]);
-              const float cmx = cm;                 // excludes element 0 of this chunk
-              cm = fmaxf(cm, x[0]);
+              const float cmx = cm * p.alpha;       // excludes element 0 of this chunk
+              cm = fmaxf(cm, x[0]) * p.alpha;
               Mx[h] = fmaxf(Mx[h], (j == 0 && c == 0) ? cmx : cm);
               const float Mn = fmaxf(M[h], cm);
               if (Mn > -INFINITY) {
                 float acc = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc += ex2_approx(x[i] - Mn);
+                for (int i = 0; i < 32; ++i) acc += ex2_approx(fmaf(x[i], p.alpha, -Mn));
                 l[h] = l[h] * ex2_approx(M[h] - Mn) + acc;
                 M[h] = Mn;
               }
@@ -448,7 +582,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         // ---- epilogue: O * out_scale (+ p0 * v0) -> out; the column splits share the dp columns
         const float oscale = MODE == DGQ_MAP_NONE ? 1.0f : delta;
-        const int head = bh % p.heads, bb = bh / p.heads;
         const int dsplit = p.dp / kSplit;         // 16-column multiples: dp = 64 / 128 / 192, kSplit = 4
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -462,57 +595,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const uint32_t on = it * nh + h, ob = on % nob;
           mbar_wait(&bars[B_OFULL + ob], (on / nob) & 1);
           tc_fence_after();
-          const size_t orow_idx = static_cast<size_t>(bb) * p.t + tq[h];
-          const size_t ooff = orow_idx * p.ldo + head * p.d;
-          __half* orow = static_cast<__half*>(p.out) + ooff;
-          float* orow32 = static_cast<float*>(p.out) + ooff;
-          float rd = 1.f, rz = 0.f, ri = 1.f;       // row-indexed / scalar output quantizer
-          if (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE) {
-            const int jq = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>(orow_idx % p.oq_period) : 0;
-            rd = __ldg(p.oq_delta + jq); rz = __ldg(p.oq_zp + jq);
-            ri = p.oq_inv != nullptr ? __ldg(p.oq_inv + jq) : rcp_rn_slow(rd);
-          }
-          for (int c = half * dsplit; c < (half + 1) * dsplit; c += 16) {
-            uint32_t r[16];
-            tmem_ld_32x16(tmem_o + ob * p.dp + lane_addr + c, r);
-            tc_wait_ld();
-            if (row_ok[h]) {
-#pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                const int d0 = c + v * 8;
-                if (d0 < p.d) {
-                  float f[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
-                    if (p.start_peak) f[i] = fmaf(pp0, v0[d0 + i], f[i]);
-                  }
-                  if (p.oq_mode == DGQ_Q_KWISE) {
-                    const int k0 = head * p.d + d0;
-                    float qd[8], qz[8], qi[8];
-                    ldg8(p.oq_delta + k0, qd);
-                    ldg8(p.oq_zp + k0, qz);
-                    if (p.oq_inv != nullptr) {
-                      ldg8(p.oq_inv + k0, qi);
-                    } else {
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) qi[i] = rcp_rn_slow(qd[i]);
-                    }
-                    uaq_lean<false, 8>(f, qd, qi, qz, p.oq_qmax);
-                  } else if (p.oq_mode != DGQ_Q_NONE) {
-                    if (p.oq_emit_int) uaq_lean1<true, 8>(f, rd, ri, rz, p.oq_qmax);
-                    else uaq_lean1<false, 8>(f, rd, ri, rz, p.oq_qmax);
-                  }
-                  if (p.out_is_f32) {
-                    *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
-                    *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
-                  } else {
-                    *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
-                  }
-                }
-              }
-            }
-          }
+          store_o(tq[h], row_ok[h], pp0, v0, oscale, ob, half * dsplit, (half + 1) * dsplit);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[B_OEMPTY + ob]);
@@ -599,26 +682,38 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   if (rc != 0) return rc;
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
-  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 2 * 192 * 4 + 3 * 128 * 4 + 64;
+  const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 4 * 192 * 4 + 3 * 128 * 4 + 64;
   AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring
   if (p1.nq_buf > 2) p1.nq_buf = 2;
   const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
   const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
-  KernelFn k1 = attention_kernel<1, 0, false>;
+  KernelFn k1 = attention_kernel<1, 0, false, false>;
   KernelFn k2;
   const bool cd = a->codes != nullptr;
+  const bool pp = p.nh == 2;            // two query halves per item: one softmax warp group per half
   switch (a->map_mode) {
-    case DGQ_MAP_LOG2: k2 = cd ? attention_kernel<2, DGQ_MAP_LOG2, true> : attention_kernel<2, DGQ_MAP_LOG2, false>; break;
-    case DGQ_MAP_UNIFORM: k2 = cd ? attention_kernel<2, DGQ_MAP_UNIFORM, true> : attention_kernel<2, DGQ_MAP_UNIFORM, false>; break;
-    default: k2 = attention_kernel<2, DGQ_MAP_NONE, false>; break;
+    case DGQ_MAP_LOG2:
+      k2 = cd ? (pp ? attention_kernel<2, DGQ_MAP_LOG2, true, true> : attention_kernel<2, DGQ_MAP_LOG2, true, false>)
+              : (pp ? attention_kernel<2, DGQ_MAP_LOG2, false, true> : attention_kernel<2, DGQ_MAP_LOG2, false, false>);
+      break;
+    case DGQ_MAP_UNIFORM:
+      k2 = cd ? (pp ? attention_kernel<2, DGQ_MAP_UNIFORM, true, true> : attention_kernel<2, DGQ_MAP_UNIFORM, true, false>)
+              : (pp ? attention_kernel<2, DGQ_MAP_UNIFORM, false, true> : attention_kernel<2, DGQ_MAP_UNIFORM, false, false>);
+      break;
+    default:
+      k2 = pp ? attention_kernel<2, DGQ_MAP_NONE, false, true> : attention_kernel<2, DGQ_MAP_NONE, false, false>;
+      break;
   }
   // every instantiation gets the maximum it can ever need once (227 KB opt-in)
   static bool attr_done = false;
   if (!attr_done) {
-    KernelFn all[] = {attention_kernel<1, 0, false>, attention_kernel<2, DGQ_MAP_LOG2, true>,
-                      attention_kernel<2, DGQ_MAP_LOG2, false>, attention_kernel<2, DGQ_MAP_UNIFORM, true>,
-                      attention_kernel<2, DGQ_MAP_UNIFORM, false>, attention_kernel<2, DGQ_MAP_NONE, false>};
+    KernelFn all[] = {attention_kernel<1, 0, false, false>,
+                      attention_kernel<2, DGQ_MAP_LOG2, true, false>, attention_kernel<2, DGQ_MAP_LOG2, true, true>,
+                      attention_kernel<2, DGQ_MAP_LOG2, false, false>, attention_kernel<2, DGQ_MAP_LOG2, false, true>,
+                      attention_kernel<2, DGQ_MAP_UNIFORM, true, false>, attention_kernel<2, DGQ_MAP_UNIFORM, true, true>,
+                      attention_kernel<2, DGQ_MAP_UNIFORM, false, false>, attention_kernel<2, DGQ_MAP_UNIFORM, false, true>,
+                      attention_kernel<2, DGQ_MAP_NONE, false, false>, attention_kernel<2, DGQ_MAP_NONE, false, true>};
     for (KernelFn f : all) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       if (e != cudaSuccess) return static_cast<int>(e);
