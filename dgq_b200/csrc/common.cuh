@@ -125,6 +125,56 @@ __device__ __forceinline__ void uaq_lean1(float (&v)[N], float delta, float inv,
   }
 }
 
+// uaq_lean with the clamp bounds folded: clamp(r + zp, 0, qmax) - zp == clamp(r, lo, hi) for lo = -zp,
+// hi = qmax - zp (r and zp are integers: the sums are exact), and the near-tie test as one FMA + compare.
+// 9 FP32 instructions per element instead of 12.
+template <int N>
+__device__ __forceinline__ void uaq_bounds(const float (&zp)[N], float qmax, float (&lo)[N], float (&hi)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) { lo[i] = -zp[i]; hi[i] = __fsub_rn(qmax, zp[i]); }
+}
+template <bool kEmitInt, int N>
+__device__ __forceinline__ void uaq_lean_lh(float (&v)[N], const float (&delta)[N], const float (&inv)[N],
+                                            const float (&lo)[N], const float (&hi)[N]) {
+  float r[N];
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float t = __fmul_rn(v[i], inv[i]);
+    r[i] = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+    near_tie |= fmaf(fabsf(t), 4.76837158e-7f, fabsf(__fsub_rn(t, r[i]))) >= 0.5f;
+  }
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = uaq_round_exact(v[i], delta[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float q = fminf(fmaxf(r[i], lo[i]), hi[i]);
+    v[i] = kEmitInt ? q : __fmul_rn(delta[i], q);
+  }
+}
+template <bool kEmitInt, int N>
+__device__ __forceinline__ void uaq_lean1_lh(float (&v)[N], float delta, float inv, float lo, float hi) {
+  float r[N];
+  bool near_tie = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float t = __fmul_rn(v[i], inv);
+    r[i] = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);
+    near_tie |= fmaf(fabsf(t), 4.76837158e-7f, fabsf(__fsub_rn(t, r[i]))) >= 0.5f;
+  }
+  if (near_tie) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = uaq_round_exact(v[i], delta);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float q = fminf(fmaxf(r[i], lo), hi);
+    v[i] = kEmitInt ? q : __fmul_rn(delta, q);
+  }
+}
+
 __device__ __forceinline__ void ldg8(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));

@@ -43,13 +43,15 @@ __device__ __forceinline__ void quant8_lean(const QuantDev& q, float (&v)[8], in
 #pragma unroll
       for (int i = 0; i < 8; ++i) inv[i] = rcp_rn_slow(d[i]);
     }
-    uaq_lean<false, 8>(v, d, inv, z, q.qmax);   // emit_int is not defined for K-wise scales
+    float lo[8], hi[8];
+    uaq_bounds<8>(z, q.qmax, lo, hi);
+    uaq_lean_lh<false, 8>(v, d, inv, lo, hi);   // emit_int is not defined for K-wise scales
   } else {
     const int j = q.mode == DGQ_Q_ROWWISE ? row % q.period : 0;
     const float dd = __ldg(q.delta + j), zz = __ldg(q.zp + j);
     const float ii = q.inv != nullptr ? __ldg(q.inv + j) : rcp_rn_slow(dd);
-    if (q.emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
-    else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
+    if (q.emit_int) uaq_lean1_lh<true, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
+    else uaq_lean1_lh<false, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
   }
 }
 
@@ -173,6 +175,8 @@ constexpr int kTileH = 8, kTileW = 16, kTileC = 64;
 template <typename TIn, int KS, int QMODE, bool kCodes>
 __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p, int tiles_x, int tiles_y) {
   constexpr int PH = kTileH + KS - 1, PW = kTileW + KS - 1;
+  // per pixel: two planes of 8 float4 -- plane q holds channels 8 s + 4 q .. + 3 of every 8-channel slot s, so the
+  // phase-2 reads (lane = slot, one float4 per plane) are 128 contiguous bytes per quarter-warp: no bank conflict
   __shared__ __align__(16) float patch[PH * PW][kTileC];
   __shared__ uint8_t inside[PH * PW];
   const int C = p.c0 + p.c1;
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
         }
         v = make_float4(u[0], u[1], u[2], u[3]);
       }
-      *reinterpret_cast<float4*>(&patch[pp][c4]) = v;
+      *reinterpret_cast<float4*>(&patch[pp][((c4 >> 2) & 1) * (kTileC / 2) + (c4 >> 3) * 4]) = v;
       if ((tid & 15) == 0) inside[pp] = in ? 1 : 0;
     }
   }
@@ -260,6 +264,8 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
 #pragma unroll
       for (int i = 0; i < 8; ++i) { d[i] = dd; z[i] = zz; inv[i] = ii; }
     }
+    float qlo[8], qhi[8];                 // clamp bounds of (code - zp), once per tap
+    if (QMODE == DGQ_Q_KWISE && !kCodes) uaq_bounds<8>(z, q.qmax, qlo, qhi);
 #pragma unroll
     for (int it = 0; it < (kTileH * kTileW) / 32; ++it) {
       const int pl = ps + it * 32;
@@ -268,8 +274,8 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
       const int pp = (pl / kTileW + dy) * PW + (pl % kTileW + dx);
       const int m = (b * p.ho + oy) * p.wo + ox;
       float v[8];
-      const float4 a0 = *reinterpret_cast<const float4*>(&patch[pp][cg]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&patch[pp][cg + 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&patch[pp][cg >> 1]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&patch[pp][(kTileC / 2) + (cg >> 1)]);
       v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
       const bool quantize = QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized);
       if (kCodes) {
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
         *reinterpret_cast<uint2*>(p.codes + static_cast<size_t>(m) * (KS * KS * C) + k0) = make_uint2(lo, hi);
       } else if (quantize) {
         if (QMODE == DGQ_Q_KWISE) {
-          uaq_lean<false, 8>(v, d, inv, z, q.qmax);
+          uaq_lean_lh<false, 8>(v, d, inv, qlo, qhi);
         } else {
           float dd = d[0], zz = z[0], ii = inv[0];
           if (QMODE == DGQ_Q_ROWWISE) {
@@ -301,8 +307,8 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
             dd = __ldg(q.delta + j); zz = __ldg(q.zp + j);
             ii = q.inv != nullptr ? __ldg(q.inv + j) : rcp_rn_slow(dd);
           }
-          if (emit_int) uaq_lean1<true, 8>(v, dd, ii, zz, q.qmax);
-          else uaq_lean1<false, 8>(v, dd, ii, zz, q.qmax);
+          if (emit_int) uaq_lean1_lh<true, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
+          else uaq_lean1_lh<false, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
         }
       }
       *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + k0) = pack8(v);
@@ -356,11 +362,22 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const TIn* __restrict__
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
     const int c = cv << 3;
-    for (int r = r0 + sub; r < r1; r += nsub) {
-      const size_t pix = static_cast<size_t>(b) * hw + r;
+    const TIn* base = c < c0 ? src0 + c : src1 + (c - c0);
+    const size_t cs = c < c0 ? c0 : c1;
+    int r = r0 + sub;
+    for (; r + 3 * nsub < r1; r += 4 * nsub) {      // four independent row loads in flight per thread
+      float v[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load8(base + (static_cast<size_t>(b) * hw + r + k * nsub) * cs, v[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += v[k][i]; q[i] += v[k][i] * v[k][i]; }
+      }
+    }
+    for (; r < r1; r += nsub) {
       float v[8];
-      if (c < c0) load8(src0 + pix * c0 + c, v);
-      else load8(src1 + pix * c1 + (c - c0), v);
+      load8(base + (static_cast<size_t>(b) * hw + r) * cs, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
     }
@@ -582,10 +599,12 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_tile_kernel(const TIn* __res
 #pragma unroll
         for (int i = 0; i < 8; ++i) inv[i] = rcp_rn_slow(d[i]);
       }
+      float qlo[8], qhi[8];
+      uaq_bounds<8>(z, q.qmax, qlo, qhi);
       for (int r = r_begin; r < r_end; ++r) {
         const float4 a0 = tile4[(r * 2 + 0) * cvec + cv], a1 = tile4[(r * 2 + 1) * cvec + cv];
         float t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        uaq_lean<false, 8>(t, d, inv, z, q.qmax);
+        uaq_lean_lh<false, 8>(t, d, inv, qlo, qhi);
         *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * c) = pack8(t);
       }
     } else {
@@ -810,7 +829,7 @@ extern "C" int dgq_gn_stats(const void* src0, const void* src1, int src_is_f32, 
   DGQ_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 && (c0 + c1) % 32 == 0);
   DGQ_CHECK_ARG(c1 == 0 || src1 != nullptr);
   DGQ_CHECK_ARG(batch > 0 && hw > 0 && (c0 + c1) <= kGnMaxC);
-  int chunks = (hw + 63) / 64;
+  int chunks = (hw + 15) / 16;           // >= 4 CTAs per SM at the SDXL sizes (scratch holds 64 chunks per sample)
   if (chunks > 64) chunks = 64;
   const int rows_per = (hw + chunks - 1) / chunks;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
