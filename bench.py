@@ -170,7 +170,9 @@ def run_cuda(args):
         breakdown = None
         if rank == 0:
             qnn.enable_cuda_graphs(False)
+            engine.OVERLAP = False        # serialised launches: per-kernel durations, not concurrent-kernel wall time
             breakdown = kernel_breakdown(torch, ops, lambda: call(devin))
+            engine.OVERLAP = True
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -193,7 +195,8 @@ def run_cuda(args):
         "data": "synthetic latents/prompt-embeddings, random-init weights, synthetic K-wise group scales",
         "config": {"workload": WORKLOAD, "global_batch": images, "parallelism": f"replica x{world}, prompt batch sharded, latents all-gathered",
                    "l2": "per-step working set (5.1 GB fp16 operands + activations) >> 126 MB L2; no flush needed",
-                   "act_dtype_between_kernels": str(ops.ACT_DTYPE).replace("torch.", ""), "cuda_graph": True},
+                   "act_dtype_between_kernels": str(ops.ACT_DTYPE).replace("torch.", ""), "cuda_graph": True,
+                   "stream_overlap": "q/k/v projections, cross-attention K/V, time-embedding projections and shortcut convs on forked streams inside the graph"},
         "e2e": {"value": round(e2e_val, 3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches_per_step * (args.steps + max(args.warmup, 3)),
         "launches_per_step": launches_per_step,
@@ -203,6 +206,8 @@ def run_cuda(args):
                      "frac": round(gemm_tflops / peak, 4), "peak_source": pk_src + " bf16 sustained (kernel timed inside a long step)",
                      "traffic": None, "share_of_step": round(gemm_ms / breakdown["_total_ms"], 4)},
         "breakdown_ms": {k: round(v["ms"], 3) for k, v in breakdown.items() if not k.startswith("_")},
+        "top_shapes_ms": {k: [round(v["ms"], 3), v["calls"]] for k, v in
+                          sorted(breakdown["_shapes"].items(), key=lambda kv: -kv[1]["ms"])[:16]},
         "step_tflops": round(2 * (QLAYER_GMAC_PER_IMAGE + ATTN_GMAC_PER_IMAGE) * 1e9 * BATCH / (ms_step / 1e3) / 1e12 * 1, 1),
     }
     line["cpu_baseline"] = cpu_baseline(torch, qnn, budget_s=float(os.environ.get("DGQ_CPU_BUDGET_S", "150"))) \
@@ -230,7 +235,18 @@ def kernel_breakdown(torch, ops, fn):
                 e0.record()
                 rc = f(*a)
                 e1.record()
-                events.append((name, e0, e1))
+                tag = name
+                try:   # per-shape rows for the two tensor-core kernels
+                    if name == "dgq_gemm_f16":
+                        t = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
+                        epi = ("plain", "geglu", "qkv")[t.epi] + ("+resid" if t.resid else "") + ("" if t.out else " f32")
+                        tag = f"gemm {t.m}x{t.n}x{t.k} {epi}"
+                    elif name == "dgq_attention":
+                        t = a[0]._obj if hasattr(a[0], "_obj") else a[0].contents
+                        tag = f"attn b{t.b} h{t.heads} t{t.t} s{t.s} d{t.d}"
+                except Exception:
+                    pass
+                events.append((name, e0, e1, tag))
                 return rc
             return g
         setattr(lib, name, wrap())
@@ -246,11 +262,18 @@ def kernel_breakdown(torch, ops, fn):
     finally:
         for name, f in originals.items():
             setattr(lib, name, f)
-    for name, e0, e1 in events:
+    shapes = {}
+    for name, e0, e1, tag in events:
+        ms = e0.elapsed_time(e1)
         d = acc.setdefault(name, {"ms": 0.0, "calls": 0})
-        d["ms"] += e0.elapsed_time(e1)
+        d["ms"] += ms
         d["calls"] += 1
+        if tag != name:
+            sh = shapes.setdefault(tag, {"ms": 0.0, "calls": 0})
+            sh["ms"] += ms
+            sh["calls"] += 1
     acc["_total_ms"] = sum(v["ms"] for v in acc.values())
+    acc["_shapes"] = shapes
     acc["_wall_ms"] = t0.elapsed_time(t1)
     return acc
 

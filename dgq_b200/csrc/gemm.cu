@@ -31,7 +31,7 @@ constexpr int kMaxBN = 256;
 // instructions per result, so with 2 warps per scheduler they, not the MMAs, bounded the tile time
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kStgLd = 36;                         // padded row stride (floats) of the fp32 epilogue transpose buffer
-constexpr int kEpiTab = 5;                         // per-column tables staged per tile
+constexpr int kEpiTab = 6;                         // per-column tables staged per tile
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
 template <int kEpi> struct EpiCfg {
   static constexpr int kWarps = kEpi == EPI_PLAIN ? 8 : 16;
@@ -53,7 +53,7 @@ template <int kCtas, int kEpi> struct GemmCfg {
   static constexpr int kStages = kCtas == 1 ? 3 : 5;
   static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  // [2 buffers][scale | bias | q.delta | 1/q.delta | q.zp][256] fp32 + one [32 rows][36] fp32 transpose
+  // [2 buffers][scale | bias | q.delta | 1/q.delta | -q.zp | qmax - q.zp][256] fp32 + one [32 rows][36] fp32 transpose
   // buffer per epilogue warp
   static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + EpiCfg<kEpi>::kWarps * EpiCfg<kEpi>::kStgBytes;
   static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -225,7 +225,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       float* s_bias = s_scale + kMaxBN;
       float* s_qd = s_bias + kMaxBN;
       float* s_qi = s_qd + kMaxBN;
-      float* s_qz = s_qi + kMaxBN;
+      float* s_qz = s_qi + kMaxBN;      // PLAIN-era name: holds lo = -zp (the fused epilogues clamp code - zp to [lo, hi])
+      float* s_qh = s_qz + kMaxBN;      // hi = qmax - zp
       for (int j = etid; j < p.bn; j += 32 * kEpiWarps) {
         const int n = ncol0 + j;
         float sc = 1.0f, bi = 0.0f;
@@ -252,7 +253,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const float dd = ok ? __ldg(q2.delta + qi) : 1.0f;
           s_qd[j] = dd;
           s_qi[j] = __frcp_rn(dd);
-          s_qz[j] = ok ? __ldg(q2.zp + qi) : 0.0f;
+          const float zz = ok ? __ldg(q2.zp + qi) : 0.0f;
+          s_qz[j] = -zz;
+          s_qh[j] = __fsub_rn(q2.qmax, zz);
         }
       }
       const char* temb_row = (p.temb != nullptr && !temb_tile && row_ok)
@@ -277,34 +280,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       const bool q_skip = kEpi == EPI_QKV && p.skip_first && tok == 0;   // start-peak: token 0 bypasses
       // quantise 32 results of this thread's row with the fused quantizer; table slots slot0 .. slot0 + 31
-      auto fused_quant32 = [&](float (&g)[32], int slot0) {
-        if (!q_on || q_skip) return;
-        const bool rw = q2.mode == DGQ_Q_ROWWISE;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          float x[8], dd[8], ii[8], zz[8], cd[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = g[v * 8 + i];
-          if (rw) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { dd[i] = qd_row; ii[i] = qi_row; zz[i] = qz_row; }
-          } else {
-#pragma unroll
-            for (int h4 = 0; h4 < 2; ++h4) {
-              const float4 a = *reinterpret_cast<const float4*>(s_qd + slot0 + v * 8 + h4 * 4);
-              const float4 b = *reinterpret_cast<const float4*>(s_qi + slot0 + v * 8 + h4 * 4);
-              const float4 c = *reinterpret_cast<const float4*>(s_qz + slot0 + v * 8 + h4 * 4);
-              dd[h4 * 4] = a.x; dd[h4 * 4 + 1] = a.y; dd[h4 * 4 + 2] = a.z; dd[h4 * 4 + 3] = a.w;
-              ii[h4 * 4] = b.x; ii[h4 * 4 + 1] = b.y; ii[h4 * 4 + 2] = b.z; ii[h4 * 4 + 3] = b.w;
-              zz[h4 * 4] = c.x; zz[h4 * 4 + 1] = c.y; zz[h4 * 4 + 2] = c.z; zz[h4 * 4 + 3] = c.w;
-            }
-          }
-          uaq_codes_rcp<8>(x, dd, ii, zz, q2.qmax, cd);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            g[v * 8 + i] = q2.emit_int ? __fsub_rn(cd[i], zz[i]) : uaq_dequant(cd[i], dd[i], zz[i]);
-        }
-      };
       // g[i] = acc[i] * row_scale * scale[n] + bias[n] for 32 consecutive tile columns j0 ..
       auto affine32 = [&](const uint32_t (&r)[32], int j0, float (&g)[32]) {
 #pragma unroll
@@ -332,32 +307,34 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
           }
         };
+        const float lo_row = -qz_row, hi_row = __fsub_rn(q2.qmax, qz_row);
         auto fused_quant16 = [&](float (&g)[16], int slot0) {
           if (!q_on || q_skip) return;
-          const bool rw = q2.mode == DGQ_Q_ROWWISE;
+          if (q2.mode == DGQ_Q_ROWWISE) {
+            if (q2.emit_int) uaq_lean1_lh<true, 16>(g, qd_row, qi_row, lo_row, hi_row);
+            else uaq_lean1_lh<false, 16>(g, qd_row, qi_row, lo_row, hi_row);
+            return;
+          }
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            float x[8], dd[8], ii[8], zz[8], cd[8];
+            float x[8], dd[8], ii[8], lo[8], hi[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = g[v * 8 + i];
-            if (rw) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { dd[i] = qd_row; ii[i] = qi_row; zz[i] = qz_row; }
-            } else {
-#pragma unroll
-              for (int h4 = 0; h4 < 2; ++h4) {
-                const float4 a = *reinterpret_cast<const float4*>(s_qd + slot0 + v * 8 + h4 * 4);
-                const float4 b = *reinterpret_cast<const float4*>(s_qi + slot0 + v * 8 + h4 * 4);
-                const float4 c = *reinterpret_cast<const float4*>(s_qz + slot0 + v * 8 + h4 * 4);
-                dd[h4 * 4] = a.x; dd[h4 * 4 + 1] = a.y; dd[h4 * 4 + 2] = a.z; dd[h4 * 4 + 3] = a.w;
-                ii[h4 * 4] = b.x; ii[h4 * 4 + 1] = b.y; ii[h4 * 4 + 2] = b.z; ii[h4 * 4 + 3] = b.w;
-                zz[h4 * 4] = c.x; zz[h4 * 4 + 1] = c.y; zz[h4 * 4 + 2] = c.z; zz[h4 * 4 + 3] = c.w;
-              }
+            for (int h4 = 0; h4 < 2; ++h4) {
+              const float4 a = *reinterpret_cast<const float4*>(s_qd + slot0 + v * 8 + h4 * 4);
+              const float4 b = *reinterpret_cast<const float4*>(s_qi + slot0 + v * 8 + h4 * 4);
+              const float4 c = *reinterpret_cast<const float4*>(s_qz + slot0 + v * 8 + h4 * 4);
+              const float4 e = *reinterpret_cast<const float4*>(s_qh + slot0 + v * 8 + h4 * 4);
+              dd[h4 * 4] = a.x; dd[h4 * 4 + 1] = a.y; dd[h4 * 4 + 2] = a.z; dd[h4 * 4 + 3] = a.w;
+              ii[h4 * 4] = b.x; ii[h4 * 4 + 1] = b.y; ii[h4 * 4 + 2] = b.z; ii[h4 * 4 + 3] = b.w;
+              lo[h4 * 4] = c.x; lo[h4 * 4 + 1] = c.y; lo[h4 * 4 + 2] = c.z; lo[h4 * 4 + 3] = c.w;
+              hi[h4 * 4] = e.x; hi[h4 * 4 + 1] = e.y; hi[h4 * 4 + 2] = e.z; hi[h4 * 4 + 3] = e.w;
             }
-            uaq_codes_rcp<8>(x, dd, ii, zz, q2.qmax, cd);
+            if (q2.emit_int) uaq_lean_lh<true, 8>(x, dd, ii, lo, hi);
+            else uaq_lean_lh<false, 8>(x, dd, ii, lo, hi);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              g[v * 8 + i] = q2.emit_int ? __fsub_rn(cd[i], zz[i]) : uaq_dequant(cd[i], dd[i], zz[i]);
+            for (int i = 0; i < 8; ++i) g[v * 8 + i] = x[i];
           }
         };
         const uint32_t t_acc = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -421,24 +398,35 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int n = kEpi == EPI_GEGLU ? n_blk * (p.bn >> 1) + c * 32 + cq : ncol0 + j0 + cq;
             const int n_lim = kEpi == EPI_GEGLU ? (p.n >> 1) : p.n;
             if (n < n_lim) {
-              int hh = 0, dd = 0;
-              if (kEpi == EPI_QKV) { hh = n / p.d; dd = n - hh * p.d; }
               const int ch = (lane & 7) >> 1, sub = (lane & 1) * 8;
+              // element offset of (row rl0 of the warp, column n); rows advance by 4: + 4 row strides, and in the
+              // head-split layout + one batch stride - `tokens` row strides when a sample boundary is crossed
+              // (offsets fit 32 bits: checked by the launcher)
+              uint32_t o, row_step;
+              int gt = 0;
+              if (kEpi == EPI_QKV) {
+                const int hh = n / p.d, dd = n - hh * p.d;
+                int gb = wbat;
+                gt = wtok + rl0;
+                while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
+                o = (static_cast<uint32_t>(gb * p.heads + hh) * p.tokens + gt) * p.dp + dd;
+                row_step = 4u * p.dp;
+              } else {
+                o = static_cast<uint32_t>(warp_row0 + rl0) * p.ldc + n;
+                row_step = 4u * p.ldc;
+              }
+              const uint32_t wrap_step = kEpi == EPI_QKV ? static_cast<uint32_t>(p.heads - 1) * p.tokens * p.dp : 0u;
 #pragma unroll
               for (int rr = 0; rr < 8; ++rr) {
                 const int rl = rr * 4 + rl0;
-                const int grow = warp_row0 + rl;
-                if (grow < p.m) {
+                if (warp_row0 + rl < p.m) {
                   const uint2 x = *reinterpret_cast<const uint2*>(stg8 + rl * 64 + ((ch ^ ((rl >> 1) & 3)) << 4) + sub);
-                  size_t o;
-                  if (kEpi == EPI_QKV) {
-                    int gb = wbat, gt = wtok + rl;          // (batch, token) of row grow, without a division
-                    while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
-                    o = ((static_cast<size_t>(gb) * p.heads + hh) * p.tokens + gt) * p.dp + dd;
-                  } else {
-                    o = static_cast<size_t>(grow) * p.ldc + n;
-                  }
                   *reinterpret_cast<uint2*>(p.out + o) = x;
+                }
+                o += row_step;
+                if (kEpi == EPI_QKV) {
+                  gt += 4;
+                  if (gt >= p.tokens) { gt -= p.tokens; o += wrap_step; }
                 }
               }
             }
@@ -539,6 +527,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
+      // ---- general plain path: edge tiles, fp16 results, per-row time-embedding rows
       if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
       epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -549,78 +538,40 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tmem_ld_32x32(t_row + j0, r);
         if (has_resid && c + 1 < c_end) load_resid(c + 1, t_nxt);
         float g[32];                        // this thread's row, 32 result columns
-        if (kEpi == EPI_GEGLU) {
-          uint32_t r2[32];
-          tmem_ld_32x32(t_row + j0 + 32, r2);
-          tc_wait_ld();
-          float x2[32];
-          affine32(r, j0, g);
-          affine32(r2, j0 + 32, x2);
+        tc_wait_ld();
+        affine32(r, j0, g);
+        if (temb_row != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] *= gelu_erf_f(x2[i]);
-          fused_quant32(g, c * 32);
-        } else {
-          tc_wait_ld();
-          affine32(r, j0, g);
-          if (temb_row != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = ncol0 + j0 + i;
-              if (n < p.n)
-                g[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n]
-                                    : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
-            }
+          for (int i = 0; i < 32; ++i) {
+            const int n = ncol0 + j0 + i;
+            if (n < p.n)
+              g[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n]
+                                  : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
           }
-          if (kEpi == EPI_QKV) fused_quant32(g, j0);
         }
-        if (kEpi == EPI_QKV && p.transpose) {
-          // V^T [b, heads, dp, tp]: for a fixed column the 32 lanes hold 32 consecutive tokens
-          if (row_ok) {
-            int n = ncol0 + j0;
-            int hh = n / p.d, dd = n - hh * p.d;
-            __half* base = p.out + (static_cast<size_t>(bat) * p.heads) * p.dp * p.tp + tok;
 #pragma unroll
-            for (int i = 0; i < 32; ++i, ++n) {
-              if (n < p.n) base[(static_cast<size_t>(hh) * p.dp + dd) * p.tp] = __float2half_rn(g[i]);
-              if (++dd == p.d) { dd = 0; ++hh; }
-            }
-          }
-        } else {
+        for (int v = 0; v < 8; ++v)
+          *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+        __syncwarp();
+        const int n = ncol0 + j0 + cq;      // result column of this lane's 4 values
+        if (n < p.n) {
 #pragma unroll
-          for (int v = 0; v < 8; ++v)
-            *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
-          __syncwarp();
-          // result column of this lane's 4 values: GEGLU feature index, otherwise the GEMM column
-          const int n = kEpi == EPI_GEGLU ? n_blk * (p.bn >> 1) + c * 32 + cq : ncol0 + j0 + cq;
-          const int n_lim = kEpi == EPI_GEGLU ? (p.n >> 1) : p.n;
-          if (n < n_lim) {
-            int hh = 0, dd = 0;
-            if (kEpi == EPI_QKV) { hh = n / p.d; dd = n - hh * p.d; }
-#pragma unroll
-            for (int rr = 0; rr < 8; ++rr) {
-              const int rl = rr * 4 + rl0;
-              const int grow = warp_row0 + rl;
-              if (grow < p.m) {
-                float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
-                if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
-                size_t o;
-                if (kEpi == EPI_QKV) {
-                  int gb = wbat, gt = wtok + rl;          // (batch, token) of row grow, without a division
-                  while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
-                  o = ((static_cast<size_t>(gb) * p.heads + hh) * p.tokens + gt) * p.dp + dd;
-                } else {
-                  o = static_cast<size_t>(grow) * p.ldc + n;
-                }
-                if (p.out != nullptr) {
-                  const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
-                  *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-                }
-                if (kEpi == EPI_PLAIN && p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+          for (int rr = 0; rr < 8; ++rr) {
+            const int rl = rr * 4 + rl0;
+            const int grow = warp_row0 + rl;
+            if (grow < p.m) {
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+              if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+              const size_t o = static_cast<size_t>(grow) * p.ldc + n;
+              if (p.out != nullptr) {
+                const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
               }
+              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
             }
           }
-          __syncwarp();
         }
+        __syncwarp();
         if (has_resid) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
@@ -741,11 +692,12 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
     DGQ_CHECK_ARG(q.mode != DGQ_Q_ROWWISE || q.period > 0);
     DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE));
   }
-  if (a->epi == DGQ_EPI_GEGLU) DGQ_CHECK_ARG(a->n % 64 == 0 && a->ldc >= a->n / 2);
+  if (a->epi == DGQ_EPI_GEGLU) DGQ_CHECK_ARG(a->n % 64 == 0 && a->ldc >= a->n / 2 && static_cast<int64_t>(a->m) * a->ldc < (int64_t(1) << 31));
   if (a->epi == DGQ_EPI_QKV) {
     DGQ_CHECK_ARG(a->heads > 0 && a->d > 0 && a->d % 8 == 0 && a->dp >= a->d && a->dp % 8 == 0);
     DGQ_CHECK_ARG(a->n == a->heads * a->d && a->tokens > 0 && a->m % a->tokens == 0);
     DGQ_CHECK_ARG(!a->transpose || (a->tp >= a->tokens && a->tp % 8 == 0));
+    DGQ_CHECK_ARG(a->tokens >= 4 && static_cast<int64_t>(a->m) * a->heads * a->dp < (int64_t(1) << 31));
   }
 
   static int force_ctas = -1;   // DGQ_GEMM_CTAS=1|2 pins the variant (benchmarking); default: by problem size
@@ -755,7 +707,8 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   }
   GemmDev p;
   p.m = a->m; p.n = a->n; p.k = a->k;
-  p.bn = pick_bn(a->n, a->epi == DGQ_EPI_GEGLU ? 64 : 32);
+  // fused epilogues split a tile's columns over 4 warps per lane quarter: widths that divide evenly
+  p.bn = pick_bn(a->n, a->epi == DGQ_EPI_PLAIN ? 32 : (a->epi == DGQ_EPI_GEGLU ? 256 : 128));
   static int force_bn = -1;     // DGQ_GEMM_BN pins the N tile (benchmarking)
   if (force_bn < 0) {
     const char* env = getenv("DGQ_GEMM_BN");

@@ -16,6 +16,7 @@ conversion, so there is exactly one compute path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -181,18 +182,51 @@ def time_mlp(emb_mod, x: torch.Tensor) -> torch.Tensor:
     return linear(emb_mod.linear_2, *quant_rows(h, emb_mod.linear_2))
 
 
-def resnet(blk, x: Act, silu_emb: torch.Tensor, x2: Optional[Act] = None) -> Act:
+def temb_prefetch(unet, silu_emb: torch.Tensor) -> dict:
+    """time_emb_proj(SiLU(temb)) of every resnet on a side stream: ~2 tiny launches per resnet that depend on
+    the time embedding only."""
+    out = {}
+    if not (OVERLAP and OVERLAP_MASK & 4):
+        return out
+    res = []
+    for blk in unet.down_blocks:
+        res += list(blk.resnets)
+    res += list(unet.mid_block.resnets)
+    for blk in unet.up_blocks:
+        res += list(blk.resnets)
+    with _Fork(silu_emb.device, 3) as f:
+        for r in res:
+            out[id(r)] = linear(r.time_emb_proj, *quant_rows(silu_emb, r.time_emb_proj))
+    out["_fork"] = f
+    return out
+
+
+def resnet(blk, x: Act, silu_emb: torch.Tensor, x2: Optional[Act] = None, te_cache: Optional[dict] = None) -> Act:
     """QuantResnetBlock2D.forward (reference quant_block.py:98-119); x2 = skip tensor to concat."""
     dev = x.t.device
-    te = linear(blk.time_emb_proj, *quant_rows(silu_emb, blk.time_emb_proj))
-    h = conv(blk.conv1, x, x2=x2, gn=_gn(blk.norm1, x, x2), act=1, temb=te)
+    te = te_cache.get(id(blk)) if te_cache else None
+    if te is not None:
+        f = te_cache.pop("_fork", None)
+        if f is not None:                 # first use: all projections are one side-stream batch
+            f.join(*[v for v in te_cache.values()])
+    else:
+        te = linear(blk.time_emb_proj, *quant_rows(silu_emb, blk.time_emb_proj))
+    fsc = None
     if blk.conv_shortcut is not None:
-        sc = conv(blk.conv_shortcut, x, x2=x2).t
+        if OVERLAP and OVERLAP_MASK & 8:  # 1x1 shortcut conv beside GroupNorm statistics + conv1
+            with _Fork(dev, 4) as fsc:
+                sc = conv(blk.conv_shortcut, x, x2=x2).t
+        else:
+            sc = conv(blk.conv_shortcut, x, x2=x2).t
     else:
         if x2 is not None:
             raise ValueError("a concatenated input needs conv_shortcut")
         sc = x.t
-    return conv(blk.conv2, h, gn=_gn(blk.norm2, h), act=1, resid=sc)
+    h = conv(blk.conv1, x, x2=x2, gn=_gn(blk.norm1, x, x2), act=1, temb=te)
+    gn2 = _gn(blk.norm2, h)
+    if fsc is not None:
+        fsc.join(sc)
+    return conv(blk.conv2, h, gn=gn2, act=1, resid=sc)
 
 
 def _attn_qparam(qt, attn, device):
@@ -235,9 +269,62 @@ def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: i
     return out
 
 
-def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torch.Tensor]) -> torch.Tensor:
+OVERLAP = True  # independent launches on forked streams: Q/K/V projections of one attention side by side
+                # (3 x 4.3 tile waves pack into 13 instead of 15), cross-attention K/V of ALL blocks on a side
+                # stream from the start of the call (they depend on the prompt embedding only)
+OVERLAP_MASK = int(os.environ.get("DGQ_OVERLAP", "15"))   # 1 q/k/v, 2 cross K/V, 4 time-embedding, 8 shortcut (A/B runs)
+_SIDE: dict = {}
+
+
+def _side_streams(dev, n: int):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+class _Fork:
+    """`with _Fork(dev, i) as f:` issues the body on side stream i, ordered after everything already on the
+    calling stream; f.join(*tensors) orders the calling stream after the body and hands tensors that were
+    allocated inside it over to the calling stream (caching-allocator bookkeeping)."""
+
+    def __init__(self, dev, idx: int):
+        self.main = torch.cuda.current_stream()
+        self.side = _side_streams(dev, idx + 1)[idx]
+        self.done = None
+
+    def __enter__(self):
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self.done = torch.cuda.Event()
+        self.done.record(self.side)
+        return self._ctx.__exit__(*exc)
+
+    def join(self, *tensors):
+        torch.cuda.current_stream().wait_event(self.done)
+        for t in tensors:
+            t.record_stream(torch.cuda.current_stream())
+
+
+def _qkv_gemm(attn, which: int, x, qin, q2, b, tok, dst, sp):
+    heads, d = attn.num_heads, attn.head_dim
+    dp = (d + 63) // 64 * 64
+    ql = (attn.to_q, attn.to_k, attn.to_v)[which]
+    _gemm(ql, x, qin, epi=ops.EPI_QKV, q2=q2, out=dst,
+          qkv=(heads, d, dp, tok, (tok + 7) // 8 * 8, which == 2, sp and which == 1))
+
+
+def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torch.Tensor], kv=None) -> torch.Tensor:
     """Attention_forward given the three already-quantised projection inputs (operands xq/xk/xv
-    written under quantizers qs = [q_to_q, q_to_k, q_to_v])."""
+    written under quantizers qs = [q_to_q, q_to_k, q_to_v]).  kv = (K, V^T, event): projections already
+    done on a side stream (cross_kv_prefetch)."""
     if not FUSE_EPILOGUES:
         q = linear(attn.to_q, xq, qs[0])
         k = linear(attn.to_k, xk, qs[1])
@@ -250,18 +337,82 @@ def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torc
     use_aq = bool(getattr(attn, "use_aq", False))
     sp = bool(getattr(attn, "start_peak", False)) and use_aq
     aq = [(_attn_qparam(getattr(attn, n), attn, dev) if use_aq else ops.NOQ) for n in ("aqtizer_q", "aqtizer_k", "aqtizer_v")]
-    ops_qkv = []
-    for ql, x, qin, q2, tok, tr, skip in ((attn.to_q, xq, qs[0], aq[0], t, False, False),
-                                         (attn.to_k, xk, qs[1], aq[1], s, False, sp),
-                                         (attn.to_v, xv, qs[2], aq[2], s, True, False)):
-        dst = ops.qkv_dest(b, tok, heads, d, dp, tr, dev)
-        _gemm(ql, x, qin, epi=ops.EPI_QKV, q2=q2, out=dst,
-              qkv=(heads, d, dp, tok, (tok + 7) // 8 * 8, tr, skip))
-        ops_qkv.append(dst)
+    main = torch.cuda.current_stream()
+    dq = ops.qkv_dest(b, t, heads, d, dp, False, dev)
+    if kv is not None:
+        dk, dv, ev = kv
+        _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
+        main.wait_event(ev)
+    else:
+        dk = ops.qkv_dest(b, s, heads, d, dp, False, dev)
+        dv = ops.qkv_dest(b, s, heads, d, dp, True, dev)
+        if OVERLAP and OVERLAP_MASK & 1:
+            s1, s2 = _side_streams(dev, 2)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for st, which, x, dst in ((s1, 1, xk, dk), (s2, 2, xv, dv)):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    _qkv_gemm(attn, which, x, qs[which], aq[which], b, s, dst, sp)
+            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
+            for st in (s1, s2):
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+        else:
+            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
+            _qkv_gemm(attn, 1, xk, qs[1], aq[1], b, s, dk, sp)
+            _qkv_gemm(attn, 2, xv, qs[2], aq[2], b, s, dv, sp)
     qo = attn.to_out[0].act_qparam(dev)
     margs = _map_args(attn, dev, sp) if use_aq else dict(map_mode=ops.MAP_NONE)
-    o, _ = ops.attention(ops_qkv[0], ops_qkv[1], ops_qkv[2], d, out_q=qo, out_emit_int=_exact(qo), **margs)
+    o, _ = ops.attention(dq, dk, dv, d, out_q=qo, out_emit_int=_exact(qo), **margs)
     return linear(attn.to_out[0], o, qo, resid=resid)
+
+
+def cross_kv_prefetch(unet, ctx: torch.Tensor) -> dict:
+    """K / V^T of every cross-attention (attn2.to_k / to_v on the prompt embedding, each under its own
+    activation quantizers) on a side stream, forked at the start of the UNet call.  These ~210 small
+    launches (77-token GEMMs: 25-50 tiles) are latency-bound; off the critical path they fill the tile-wave
+    tails of the main stream's kernels.  Destination buffers are allocated on the calling stream."""
+    out = {}
+    if not (OVERLAP and OVERLAP_MASK & 2 and FUSE_EPILOGUES) or ctx is None:
+        return out
+    t2d = []                              # Transformer2DModels in execution order
+    for blk in unet.down_blocks:
+        t2d += list(getattr(blk, "attentions", None) or [])
+    t2d += list(unet.mid_block.attentions)
+    for blk in unet.up_blocks:
+        t2d += list(getattr(blk, "attentions", None) or [])
+    blocks = [tb for m in t2d for tb in m.transformer_blocks]
+    if not blocks:
+        return out
+    dev = ctx.device
+    main = torch.cuda.current_stream()
+    cx, cb, s = _ctx_operand(ctx)
+    side = _side_streams(dev, 3)[2]
+    dests = []
+    for blk in blocks:
+        a2 = blk.attn2
+        heads, d = a2.num_heads, a2.head_dim
+        dp = (d + 63) // 64 * 64
+        dests.append((ops.qkv_dest(cb, s, heads, d, dp, False, dev), ops.qkv_dest(cb, s, heads, d, dp, True, dev)))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        for blk, (dk, dv) in zip(blocks, dests):
+            a2 = blk.attn2
+            use_aq = bool(getattr(a2, "use_aq", False))
+            sp = bool(getattr(a2, "start_peak", False)) and use_aq
+            qs = [None, a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
+            aq = [None] + [(_attn_qparam(getattr(a2, n), a2, dev) if use_aq else ops.NOQ) for n in ("aqtizer_k", "aqtizer_v")]
+            xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
+            _qkv_gemm(a2, 1, xkv[0], qs[1], aq[1], cb, s, dk, sp)
+            _qkv_gemm(a2, 2, xkv[1], qs[2], aq[2], cb, s, dv, sp)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            out[id(a2)] = (dk, dv, ev)
+    return out
 
 
 def _ctx_operand(ctx: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
@@ -272,7 +423,7 @@ def _ctx_operand(ctx: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
     return x.contiguous(), b, s
 
 
-def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor]) -> Act:
+def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor], kv_cache: Optional[dict] = None) -> Act:
     """QuantBasicTransformerBlock.forward (reference quant_block.py:165-186)."""
     dev = h.t.device
     b, t = h.b, h.rows
@@ -285,8 +436,12 @@ def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor]) -> Act:
         qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
         xq = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs[:1],
                           emit_int=EXACT_INT)[0]
-        xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
-        x = attention(a2, xq, xkv[0], xkv[1], qs, b, t, s, resid=x)
+        kv = kv_cache.get(id(a2)) if kv_cache else None
+        if kv is not None:
+            x = attention(a2, xq, None, None, qs, b, t, s, resid=x, kv=kv)
+        else:
+            xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
+            x = attention(a2, xq, xkv[0], xkv[1], qs, b, t, s, resid=x)
     else:
         qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
         xs = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs, emit_int=EXACT_INT)
@@ -303,7 +458,7 @@ def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor]) -> Act:
     return Act(x, h.b, h.h, h.w)
 
 
-def transformer2d(mod, x: Act, ctx: Optional[torch.Tensor]) -> Act:
+def transformer2d(mod, x: Act, ctx: Optional[torch.Tensor], kv_cache: Optional[dict] = None) -> Act:
     """Transformer2DModel.forward (sd.py:283-305 conv proj; sdxl.py:306-326 linear proj): in NHWC
     both are the same GEMM, and the NCHW<->token permutes of the reference disappear."""
     dev = x.t.device
@@ -315,7 +470,7 @@ def transformer2d(mod, x: Act, ctx: Optional[torch.Tensor]) -> Act:
                                 emit_int=_exact(qi))
         h = Act(linear(mod.proj_in, a_op, qi), x.b, x.h, x.w)
     for blk in mod.transformer_blocks:
-        h = transformer_block(blk, h, ctx)
+        h = transformer_block(blk, h, ctx, kv_cache)
     if mod.proj_out.is_conv:
         return conv(mod.proj_out, h, resid=x.t)
     y = linear(mod.proj_out, *quant_rows(h.t, mod.proj_out), resid=x.t)
@@ -347,16 +502,18 @@ def unet_forward(unet, sample: torch.Tensor, timesteps: torch.Tensor, ctx: torch
     silu_emb = ops.silu(emb)  # nonlinearity(temb) is the same tensor for every resnet
 
     _tap("emb", emb)
+    kvc = cross_kv_prefetch(unet, ctx)
+    tec = temb_prefetch(unet, silu_emb)
     h = conv(unet.conv_in, act_from_nchw(sample))
     _tap("conv_in", h)
     skips: List[Act] = [h]
     for i, blk in enumerate(unet.down_blocks):
         attns = getattr(blk, "attentions", None)
         for j, res in enumerate(blk.resnets):
-            h = resnet(res, h, silu_emb)
+            h = resnet(res, h, silu_emb, te_cache=tec)
             _tap(f"down{i}.res{j}", h)
             if attns is not None:
-                h = transformer2d(attns[j], h, ctx)
+                h = transformer2d(attns[j], h, ctx, kvc)
                 _tap(f"down{i}.attn{j}", h)
             skips.append(h)
         if getattr(blk, "downsamplers", None) is not None:
@@ -364,19 +521,19 @@ def unet_forward(unet, sample: torch.Tensor, timesteps: torch.Tensor, ctx: torch
             skips.append(h)
 
     mid = unet.mid_block
-    h = resnet(mid.resnets[0], h, silu_emb)
+    h = resnet(mid.resnets[0], h, silu_emb, te_cache=tec)
     for attn, res in zip(mid.attentions, mid.resnets[1:]):
-        h = transformer2d(attn, h, ctx)
-        h = resnet(res, h, silu_emb)
+        h = transformer2d(attn, h, ctx, kvc)
+        h = resnet(res, h, silu_emb, te_cache=tec)
     _tap("mid", h)
 
     for i, blk in enumerate(unet.up_blocks):
         attns = getattr(blk, "attentions", None)
         for j, res in enumerate(blk.resnets):
-            h = resnet(res, h, silu_emb, x2=skips.pop())  # torch.cat([h, skip], 1) fused into the producers
+            h = resnet(res, h, silu_emb, x2=skips.pop(), te_cache=tec)  # torch.cat([h, skip], 1) fused into the producers
             _tap(f"up{i}.res{j}", h)
             if attns is not None:
-                h = transformer2d(attns[j], h, ctx)
+                h = transformer2d(attns[j], h, ctx, kvc)
                 _tap(f"up{i}.attn{j}", h)
         if getattr(blk, "upsamplers", None) is not None:
             for up in blk.upsamplers:
