@@ -204,7 +204,9 @@ def run_cuda(args):
         "roofline": {"kernel": "gemm_f16_kernel (tcgen05 qGEMM, all 794 QuantLayers)", "bound": "tensor",
                      "achieved": round(gemm_tflops, 1), "peak": peak, "unit": "TFLOP/s",
                      "frac": round(gemm_tflops / peak, 4), "peak_source": pk_src + " bf16 sustained (kernel timed inside a long step)",
-                     "traffic": None, "share_of_step": round(gemm_ms / breakdown["_total_ms"], 4)},
+                     "traffic": ncu_traffic(),
+                     "traffic_note": "dram read+write bytes of ONE captured launch (16384x10240x1280, fp16 out; 403 MB algorithmic), profiles/r1e_gemm_f16_full.txt; tensor pipe active 90.5 % in that launch",
+                     "share_of_step": round(gemm_ms / breakdown["_total_ms"], 4)},
         "breakdown_ms": {k: round(v["ms"], 3) for k, v in breakdown.items() if not k.startswith("_")},
         "top_shapes_ms": {k: [round(v["ms"], 3), v["calls"]] for k, v in
                           sorted(breakdown["_shapes"].items(), key=lambda kv: -kv[1]["ms"])[:16]},
@@ -215,6 +217,22 @@ def run_cuda(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes (read + write) of the captured qGEMM launch in the committed `ncu --set full` summary
+    (profiles/r1e_gemm_f16_full.txt: 16384 x 10240 x 1280, fp16 result; algorithmic bytes 403 MB)."""
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", "r1e_gemm_f16_full.txt")):
+            t = line.split()
+            if len(t) >= 3 and t[0] == "dram__bytes_read.sum" and rd is None:
+                rd = float(t[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+            if len(t) >= 3 and t[0] == "dram__bytes_write.sum" and wr is None:
+                wr = float(t[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+        return None if rd is None or wr is None else round(rd + wr)
+    except Exception:
+        return None
 
 
 def kernel_breakdown(torch, ops, fn):

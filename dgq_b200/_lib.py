@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libdgq_b200.so")
 
 SYMBOLS = [
-    "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight",
+    "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight", "dgq_unpack_weight",
     "dgq_act_producer", "dgq_gn_stats", "dgq_ln_quant", "dgq_row_quant", "dgq_geglu_quant",
     "dgq_gemm_f16", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
     "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add", "dgq_sampler_step",
@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
             "dgq_t2i_log_quant_f32": [vp, i64, vp, f, vp, vp, vp],
             "dgq_max_f32": [vp, i64, vp, vp, vp],
             "dgq_pack_weight": [vp, vp, vp, vp, i, i, i, i, i, f, i, vp, vp, vp, vp],
+            "dgq_unpack_weight": [vp, i, vp, i, i, i, i, i, vp, vp],
             "dgq_act_producer": [C.POINTER(ProducerT), vp],
             "dgq_gn_stats": [vp, vp, i, i, i, i, i, f, vp, vp, vp, vp],
             "dgq_ln_quant": [vp, i, i, i, vp, vp, f, i, C.POINTER(QuantT), C.POINTER(vp), vp],

@@ -139,6 +139,25 @@ __global__ void pack_nibbles_kernel(const uint8_t* __restrict__ codes, int64_t n
     out[i] = static_cast<uint8_t>((codes[2 * i] & 0xF) | (codes[2 * i + 1] << 4));
 }
 
+// compiled-checkpoint load path: integer codes (one per byte, or two 4-bit codes per byte, low nibble first)
+// -> the resident fp16 operand (code - zp), zero in the padded rows / channels
+__global__ void unpack_weight_kernel(const uint8_t* __restrict__ codes, int bits, const float* __restrict__ zp, int n,
+                                     int ci, int taps, int ci_pad, int n_pad, __half* __restrict__ operand) {
+  const int k_out = taps * ci_pad;
+  const int64_t total = static_cast<int64_t>(n_pad) * k_out;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int row = static_cast<int>(i / k_out);
+    const int c = static_cast<int>(i % k_out) % ci_pad;
+    float op = 0.0f;
+    if (row < n && c < ci) {
+      const uint32_t code = bits == 4 ? ((codes[i >> 1] >> ((i & 1) * 4)) & 0xFu) : codes[i];
+      op = static_cast<float>(code) - zp[row];
+    }
+    operand[i] = __float2half_rn(op);
+  }
+}
+
 static int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g < 1) g = 1;
@@ -195,5 +214,17 @@ extern "C" int dgq_pack_weight(const float* w, const float* delta, const float* 
       w, delta, zp, alpha, n, ci, taps, ci_pad, n_pad, qmax, use_wq, codes, static_cast<__half*>(operand));
   if (packed4 != nullptr)
     pack_nibbles_kernel<<<grid_for(total / 2, 256, kNumSMs * 16), 256, 0, s>>>(codes, total / 2, packed4);
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_unpack_weight(const uint8_t* codes, int bits, const float* zp, int n, int ci, int taps, int ci_pad,
+                                 int n_pad, void* operand, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(codes != nullptr && zp != nullptr && operand != nullptr);
+  DGQ_CHECK_ARG((bits == 4 || bits == 8) && n > 0 && ci > 0 && taps > 0 && ci_pad >= ci && n_pad >= n);
+  DGQ_CHECK_ARG(bits == 8 || (static_cast<int64_t>(taps) * ci_pad) % 2 == 0);
+  const int64_t total = static_cast<int64_t>(n_pad) * taps * ci_pad;
+  unpack_weight_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      codes, bits, zp, n, ci, taps, ci_pad, n_pad, static_cast<__half*>(operand));
   DGQ_RETURN_LAST_ERROR();
 }

@@ -156,6 +156,18 @@ def pack_weight(w: torch.Tensor, delta, zp, alpha, qmax: float, use_wq: bool, *,
     return operand, codes, packed
 
 
+def unpack_weight(codes: torch.Tensor, bits: int, zp: torch.Tensor, n: int, ci: int, taps: int, ci_pad: int,
+                  n_pad: int) -> torch.Tensor:
+    """compiled-checkpoint codes (uint8; two per byte when bits == 4) -> resident fp16 operand (code - zp)."""
+    assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+    operand = torch.empty(n_pad, taps * ci_pad, dtype=torch.float16, device=codes.device)
+    z = _f32(zp, codes.device).reshape(-1)
+    L.check(L.lib().dgq_unpack_weight(_p(codes), bits, _p(z), n, ci, taps, ci_pad, n_pad, _p(operand), _stream()),
+            "dgq_unpack_weight")
+    _count()
+    return operand
+
+
 def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Optional[torch.Tensor] = None,
                  upsample: bool = False, ksize: int = 1, stride: int = 1, gn=None, act: int = 0,
                  q: QParam = NOQ, pad_quantized: bool = False, ldo: Optional[int] = None,

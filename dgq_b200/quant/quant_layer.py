@@ -238,6 +238,7 @@ class QuantLayer(nn.Module):
         self.extra_repr = layer.extra_repr
         self.use_group_num = False
         self._pack = None
+        self._frozen = None   # (operand, scale, bias, n_pad) installed by dgq_b200.compiled.load_compiled
 
     # -- geometry -----------------------------------------------------------------------------
     @property
@@ -268,6 +269,8 @@ class QuantLayer(nn.Module):
     def packed(self, geglu: bool = False):
         """(operand fp16 [n_pad, K], scale fp32 [n_pad] | None, bias fp32 [n_pad] | None, n_pad).
         geglu: rows interleaved for the fused GEGLU epilogue (cached separately)."""
+        if self._frozen is not None:
+            return self._frozen_pack(geglu)
         w = self.w if self.use_wq else self.original_w
         b = self.b if self.use_wq else self.original_b
         _need_cuda(w, "QuantLayer weights")
@@ -314,6 +317,23 @@ class QuantLayer(nn.Module):
             self._pack = {}
         self._pack[geglu] = (key, (operand, scale, bias, n_pad))
         return self._pack[geglu][1]
+
+    def _frozen_pack(self, geglu: bool):
+        """Operands of a compiled checkpoint (no fp32 master weights on the device)."""
+        if not geglu:
+            return self._frozen
+        hit = self._pack.get("frozen_geglu") if self._pack else None
+        if hit is None:
+            operand, scale, bias, n_pad = self._frozen
+            n = self.out_features
+            if n % 64 or n_pad != n:
+                raise ValueError("GEGLU interleave needs 2f to be a multiple of 64")
+            i = torch.arange(n, device=operand.device)
+            perm = (i // 64) * 32 + i % 32 + ((i % 64) >= 32) * (n // 2)
+            hit = (operand[perm].contiguous(), None if scale is None else scale[perm].contiguous(),
+                   None if bias is None else bias[perm].contiguous(), n_pad)
+            self._pack = dict(self._pack or {}, frozen_geglu=hit)
+        return hit
 
     def packed_int4(self):
         """The W4 checkpoint payload: two codes per byte + per-channel (delta, zp) -- 0.5 B/weight."""

@@ -39,6 +39,12 @@ class QuantModel(nn.Module):
         if hasattr(model.config, "addition_time_embed_dim"):
             self.config.addition_time_embed_dim = model.config.addition_time_embed_dim
         self.tib_recon = tib_recon
+        # constructor arguments and raw activation tables, kept for dgq_b200.compiled.compile_checkpoint
+        self._ctor = {"wbits": wq_params.get("bits"), "abits": aq_params.get("bits"),
+                      "softmax": {k: softmax_aq_params.get(k) for k in
+                                  ("softmax_a_bit", "t2i_log_quant", "t2i_real_time", "t2i_start_peak", "log_max_1")}}
+        self._raw_tables = None
+        self._device = None
         self.B = b2qb()
         self.quant_module(self.model, wq_params, aq_params,
                           aq_mode=kwargs.get("aq_mode", [QMODE.NORMAL.value]), prev_name=None)
@@ -87,6 +93,7 @@ class QuantModel(nn.Module):
         gets one device QParam per step; the sticky use_group_num flip of the reference's loader
         (quant/calibration.py:271-278) is replayed per step, in step order."""
         dev = self.device
+        self._raw_tables = tables
         named = dict(self.named_modules())
         qtables: Dict[str, list] = {}
         flips: List[List[str]] = []
@@ -204,4 +211,6 @@ class QuantModel(nn.Module):
 
     @property
     def device(self):
+        if self._device is not None:      # compiled checkpoints keep no master weights (meta parameters)
+            return self._device
         return next(self.parameters()).device

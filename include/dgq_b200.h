@@ -79,6 +79,13 @@ int dgq_pack_weight(const float* w, const float* delta, const float* zp, const f
                     int ci, int taps, int ci_pad, int n_pad, float qmax, int use_wq, uint8_t* codes,
                     uint8_t* packed4, void* operand, void* stream);
 
+/* ---- compiled-checkpoint load (replaces the fp32 pickle + per-load re-quantisation of
+ *      quant/calibration.py:208-251): codes [n_pad, taps*ci_pad] (bits == 8) or two codes per byte, low
+ *      nibble first (bits == 4) as written by dgq_pack_weight -> operand fp16 = code - zp[row]
+ *      (0 in the padded rows / channels).                                                            */
+int dgq_unpack_weight(const uint8_t* codes, int bits, const float* zp, int n, int ci, int taps, int ci_pad,
+                      int n_pad, void* operand, void* stream);
+
 /* ---- activation producer: fused [concat] -> [nearest x2] -> [GroupNorm] -> [SiLU] -> im2col ->
  *      UniformAffineQuantizer, emitting the fp16 A operand of the following GEMM ----------------
  * Replaces F.unfold + aqtizer (quant/quant_layer.py:630-641), GroupNorm+SiLU

@@ -191,3 +191,17 @@ def test_sharded_gather_world2_gloo(tmp_path):
         want = bench.make_inputs(torch, 2, seed=1000 + rank)[0][:, :, :2, :2]
         assert torch.equal(r["g"][rank], want)
     assert not torch.equal(r["g"][0], r["g"][1])
+
+
+def test_compiled_header_rejects_foreign_files(tmp_path):
+    """compiled-checkpoint reader (host logic only): magic / format checks"""
+    from dgq_b200 import compiled
+    p = tmp_path / "x.dgqb"
+    p.write_bytes(b"not a checkpoint at all" * 4)
+    with pytest.raises(ValueError):
+        compiled.read_header(str(p))
+    import json, struct
+    hj = json.dumps({"format": 99}).encode()
+    p.write_bytes(compiled.MAGIC + struct.pack("<Q", len(hj)) + hj)
+    with pytest.raises(ValueError):
+        compiled.read_header(str(p))
