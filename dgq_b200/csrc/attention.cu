@@ -327,48 +327,59 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
       // O accumulator `ob`, columns [c_lo, c_hi) of this thread's row: O * out_scale (+ p0 * v0), the to_out quantizer, store
       const int head = bh % p.heads, bb = bh / p.heads;
-      auto store_o = [&](int tqh, bool rok, float pp0, const float* v0, float oscale, uint32_t ob, int c_lo, int c_hi) {
+      // `stage` != nullptr (ping-pong path): results go through a 4 KB per-warp, XOR-swizzled shared-memory tile
+      // (carved from the group's idle P' buffer) and leave as 128-byte (fp32) / 64-byte (fp16) row segments;
+      // thread-per-row stores of 16 bytes cost 32 L1 wavefronts per instruction and made this epilogue 40-45 % of
+      // the cross-attention kernels.
+      auto store_o = [&](int tqh, bool rok, float pp0, const float* v0, float oscale, uint32_t ob, int c_lo, int c_hi,
+                         uint8_t* stage) {
           const size_t orow_idx = static_cast<size_t>(bb) * p.t + tqh;
           const size_t ooff = orow_idx * p.ldo + head * p.d;
           __half* orow = static_cast<__half*>(p.out) + ooff;
           float* orow32 = static_cast<float*>(p.out) + ooff;
           float rd = 1.f, rz = 0.f, ri = 1.f;       // row-indexed / scalar output quantizer
-          if (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE) {
+          if (rok && (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE)) {
             const int jq = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>(orow_idx % p.oq_period) : 0;
             rd = __ldg(p.oq_delta + jq); rz = __ldg(p.oq_zp + jq);
             ri = p.oq_inv != nullptr ? __ldg(p.oq_inv + jq) : rcp_rn_slow(rd);
           }
+          const int rows_ok = p.t - (tqh - lane);   // rows of this warp's 32 that exist (tqh - lane = its first query row)
           for (int c = c_lo; c < c_hi; c += 16) {
             uint32_t r[16];
             tmem_ld_32x16(tmem_o + ob * p.dp + lane_addr + c, r);
             tc_wait_ld();
-            if (rok) {
 #pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                const int d0 = c + v * 8;
-                if (d0 < p.d) {
-                  float f[8];
+            for (int v = 0; v < 2; ++v) {
+              const int d0 = c + v * 8;
+              float f[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
-                    if (p.start_peak) f[i] = fmaf(pp0, v0[d0 + i], f[i]);
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+              if (rok && d0 < p.d) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  f[i] = __uint_as_float(r[v * 8 + i]) * oscale;
+                  if (p.start_peak) f[i] = fmaf(pp0, v0[d0 + i], f[i]);
+                }
+                if (p.oq_mode == DGQ_Q_KWISE) {
+                  const int k0 = head * p.d + d0;
+                  float qd[8], qz[8], qi[8], lo[8], hi[8];
+                  ldg8(p.oq_delta + k0, qd);
+                  ldg8(p.oq_zp + k0, qz);
+                  if (p.oq_inv != nullptr) {
+                    ldg8(p.oq_inv + k0, qi);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) qi[i] = rcp_rn_slow(qd[i]);
                   }
-                  if (p.oq_mode == DGQ_Q_KWISE) {
-                    const int k0 = head * p.d + d0;
-                    float qd[8], qz[8], qi[8];
-                    ldg8(p.oq_delta + k0, qd);
-                    ldg8(p.oq_zp + k0, qz);
-                    if (p.oq_inv != nullptr) {
-                      ldg8(p.oq_inv + k0, qi);
-                    } else {
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) qi[i] = rcp_rn_slow(qd[i]);
-                    }
-                    uaq_lean<false, 8>(f, qd, qi, qz, p.oq_qmax);
-                  } else if (p.oq_mode != DGQ_Q_NONE) {
-                    if (p.oq_emit_int) uaq_lean1<true, 8>(f, rd, ri, rz, p.oq_qmax);
-                    else uaq_lean1<false, 8>(f, rd, ri, rz, p.oq_qmax);
-                  }
+                  uaq_bounds<8>(qz, p.oq_qmax, lo, hi);
+                  uaq_lean_lh<false, 8>(f, qd, qi, lo, hi);
+                } else if (p.oq_mode != DGQ_Q_NONE) {
+                  if (p.oq_emit_int) uaq_lean1_lh<true, 8>(f, rd, ri, -rz, __fsub_rn(p.oq_qmax, rz));
+                  else uaq_lean1_lh<false, 8>(f, rd, ri, -rz, __fsub_rn(p.oq_qmax, rz));
+                }
+              }
+              if (stage == nullptr) {
+                if (rok && d0 < p.d) {
                   if (p.out_is_f32) {
                     *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
                     *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
@@ -376,7 +387,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
                   }
                 }
+              } else {
+                const int j8 = ((c - c_lo) & 16) / 8 + v;            // 8-column group inside the 32-column block
+                if (p.out_is_f32) {
+                  *reinterpret_cast<float4*>(stage + lane * 128 + (((2 * j8) ^ (lane & 7)) << 4)) = make_float4(f[0], f[1], f[2], f[3]);
+                  *reinterpret_cast<float4*>(stage + lane * 128 + (((2 * j8 + 1) ^ (lane & 7)) << 4)) = make_float4(f[4], f[5], f[6], f[7]);
+                } else {
+                  *reinterpret_cast<uint4*>(stage + lane * 64 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = pack8(f);
+                }
               }
+            }
+            if (stage != nullptr && (((c - c_lo) & 16) != 0 || c + 16 >= c_hi)) {
+              // a 32-column block (or the tail) is staged: write it out as row segments
+              const int cb = c_lo + ((c - c_lo) & ~31);              // first column of the block
+              __syncwarp();
+              // element offset of (row 0 of this warp, column cb) from this thread's own row pointer
+              const ptrdiff_t row0 = -static_cast<ptrdiff_t>(lane) * p.ldo;
+              if (p.out_is_f32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = i * 4 + (lane >> 3), ch = lane & 7;
+                  const float4 x = *reinterpret_cast<const float4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                  const int col = cb + ch * 4;
+                  if (rr < rows_ok && col < c_hi && col < p.d)
+                    *reinterpret_cast<float4*>(orow32 + row0 + static_cast<ptrdiff_t>(rr) * p.ldo + col) = x;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+                  const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+                  const int col = cb + ch * 8;
+                  if (rr < rows_ok && col < c_hi && col < p.d)
+                    *reinterpret_cast<uint4*>(orow + row0 + static_cast<ptrdiff_t>(rr) * p.ldo + col) = x;
+                }
+              }
+              __syncwarp();
             }
           }
       };
@@ -446,7 +492,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(&bars[B_OFULL + ob], it & 1);
         tc_fence_after();
         const int dsplit = p.dp >> 1;
-        store_o(tqh, rok, pp0, v0, MODE == DGQ_MAP_NONE ? 1.0f : delta, ob, half * dsplit, (half + 1) * dsplit);
+        // staging tile: this warp's 4 KB of the group's P' buffer (every PV of the item has retired: OFULL)
+        uint8_t* stage = s_p + grp * 2 * kChunkBytes + ((warp - Cfg::kFirstSoftmaxWarp) & 7) * 4096;
+        store_o(tqh, rok, pp0, v0, MODE == DGQ_MAP_NONE ? 1.0f : delta, ob, half * dsplit, (half + 1) * dsplit, stage);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_OEMPTY + ob]);
@@ -595,7 +643,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const uint32_t on = it * nh + h, ob = on % nob;
           mbar_wait(&bars[B_OFULL + ob], (on / nob) & 1);
           tc_fence_after();
-          store_o(tq[h], row_ok[h], pp0, v0, oscale, ob, half * dsplit, (half + 1) * dsplit);
+          store_o(tq[h], row_ok[h], pp0, v0, oscale, ob, half * dsplit, (half + 1) * dsplit, nullptr);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[B_OEMPTY + ob]);
