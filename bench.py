@@ -24,6 +24,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
 MODEL, WBITS, ABITS, GROUPS, BATCH = "sdxl", 4, 8, 16, 16
 QLAYER_GMAC_PER_IMAGE = 2988.66      # QuantLayer GEMM MACs per sample per UNet call (SDXL)

@@ -312,7 +312,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map
         out = torch.empty(b * t, heads * d, dtype=out_dtype, device=dev)
     row_max = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
     row_sum = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
-    gmax = torch.zeros(1 + 1024, dtype=torch.float32, device=dev)
+    # gmax[0]: real-time delta, zeroed by dgq_attention itself (a memset node, not an extra fill kernel)
+    gmax = torch.empty(1, dtype=torch.float32, device=dev) if real_time else torch.zeros(1, dtype=torch.float32, device=dev)
     codes = torch.zeros(b, heads, t, s, dtype=torch.uint8, device=dev) if want_codes else None
     a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
                 int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0),

@@ -261,9 +261,13 @@ class QuantLayer(nn.Module):
         """reference unfold order (c*k*k + tap) -> GEMM K order (tap*C_pad + c)."""
         if not self.is_conv or self.ksize == 1:
             return None
-        ci, kk = self.w.shape[1], self.ksize * self.ksize
-        return (torch.arange(ci, device=device).view(1, ci) * kk
-                + torch.arange(kk, device=device).view(kk, 1)).reshape(-1)
+        hit = self.__dict__.get("_kperm_cache")
+        if hit is None or hit[0] != str(device):   # built once: three tiny kernels per conv per call otherwise
+            ci, kk = self.w.shape[1], self.ksize * self.ksize
+            hit = (str(device), (torch.arange(ci, device=device).view(1, ci) * kk
+                                 + torch.arange(kk, device=device).view(kk, 1)).reshape(-1))
+            self.__dict__["_kperm_cache"] = hit
+        return hit[1]
 
     # -- packed weights (K2: once, not per forward) -----------------------------------------
     def packed(self, geglu: bool = False):
@@ -351,6 +355,8 @@ class QuantLayer(nn.Module):
         if self.aqtizer._table is None and self.aqtizer.delta is None:
             raise RuntimeError("activation quantizer has no parameters: load a calibration checkpoint "
                                "(quant.load_qmodel_util.get_qmodel) or run the stand-alone forward once")
+        if self.aqtizer._table is not None:        # time-aware: device tables already in GEMM K order
+            return self.aqtizer._table[self.aqtizer._step]
         return self.aqtizer.qparam(device, conv=self.is_conv, kperm=self._kperm(device))
 
     @property

@@ -200,7 +200,7 @@ typedef struct {
   float qmax;
   float* row_max;       /* scratch [b*heads*t] */
   float* row_sum;       /* scratch [b*heads*t] */
-  float* gmax;          /* scratch [1 + 1024]; gmax[0] receives the real-time delta */
+  float* gmax;          /* [1]: receives the real-time delta (zeroed by the call itself)  */
   void* out;            /* [b*t, ldo], head h at columns h*d .. h*d+d-1; fp32 when out_is_f32 */
   int ldo;
   int out_is_f32;
