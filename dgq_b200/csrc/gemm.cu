@@ -296,15 +296,23 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ---- fused epilogues (16 warps: thread = one row x a quarter of the tile's columns).  A unit of 32
         // results is produced in two batches of 16 (register budget: 112 per thread at 576 threads), packed to
         // fp16, transposed through a swizzled 2 KB per-warp buffer and stored as 64-byte row segments.
+        const bool has_rs = p.row_scale != nullptr;   // K-wise A operands carry their delta: no row scale
         auto affine16 = [&](const uint32_t (&r)[16], int j0, float (&g)[16]) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
             const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
-            g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
-            g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
-            g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
-            g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+            if (has_rs) {
+              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
+              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
+              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
+              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+            } else {
+              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]), sc.x, bi.x);
+              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]), sc.y, bi.y);
+              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]), sc.z, bi.z);
+              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]), sc.w, bi.w);
+            }
           }
         };
         const float lo_row = -qz_row, hi_row = __fsub_rn(q2.qmax, qz_row);
