@@ -90,6 +90,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= 0 on the FMA pipe (Cody-Waite split + degree-6 Taylor of 2^f on [-0.5, 0.5]: relative error
+// 1.2e-7, the level of ex2.approx): pass 1 is bound by the 16-lane MUFU pipe (ncu: XU 80 % busy, issue 50 %),
+// so one exponential in four is computed here instead (~11 FMA/ALU instructions) and the two pipes finish together.
+constexpr int kPolyEvery = 6;   // pass 1: one exponential in kPolyEvery goes to the FMA pipe
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);                       // masked scores are -inf
+  const float t = x + 12582912.0f;             // integer part in the low mantissa bits
+  const float f = x - (t - 12582912.0f);       // [-0.5, 0.5]
+  float p = 1.5403530e-4f;
+  p = fmaf(p, f, 1.33335581e-3f);
+  p = fmaf(p, f, 9.61812911e-3f);
+  p = fmaf(p, f, 5.550410866e-2f);
+  p = fmaf(p, f, 2.4022650696e-1f);
+  p = fmaf(p, f, 6.9314718056e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 template <int kThreads> __device__ __forceinline__ void softmax_bar_sync(int id = 1) {  // the softmax warps only
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
@@ -540,7 +557,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               if (Mn > -INFINITY) {
                 float acc = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc += ex2_approx(fmaf(x[i], p.alpha, -Mn));
+                for (int i = 0; i < 32; ++i) {
+                  const float e = fmaf(x[i], p.alpha, -Mn);
+                  acc += (i % kPolyEvery) == kPolyEvery - 1 ? ex2_poly(e) : ex2_approx(e);
+                }
                 l[h] = l[h] * ex2_approx(M[h] - Mn) + acc;
                 M[h] = Mn;
               }
