@@ -16,16 +16,15 @@
 //   log2 map : code = clamp(rint(beta_i + log2(delta) - s*alpha), 0, qmax),  P' = 2^-code
 //   uniform  : code = clamp(rint(2^(s*alpha - beta_i - log2(delta))), 0, qmax), P' = code
 //
-// PERSISTENT CTAs: a work item is one 128-row query tile of one (batch, head); CTA c runs items
-// c, c + grid, ... as ONE continuous pipeline -- the K/V ring, the double-buffered S and P tiles, a
-// double-buffered Q tile and a double-buffered O accumulator all carry over from item to item, so the
-// QK^T of the next item overlaps the softmax / PV / epilogue of the current one (cross-attention,
-// S = 77, is a single K tile per item: without this it is launch- and latency-bound).
-// 320 threads:
-//   warp 0 TMA loader | warp 1 MMA issuer (one lane) | warps 2..9 softmax: thread = (row, column half)
-//   (TMEM lane == row, so row reductions need no shuffles).
-// TMEM: S 2 x 128 columns + O 1-2 x dp columns.  P' goes through smem in the UMMA K-major
-// 128B-swizzle layout, written by the softmax threads.
+// PERSISTENT CTAs: a work item is one or two 128-row query tiles ("halves") of one (batch, head); CTA c runs
+// items c, c + grid, ... as ONE continuous pipeline -- the K/V rings, the S and P' buffers, the Q ring and the
+// O accumulators all carry over from item to item, so the QK^T of the next item overlaps the softmax / PV /
+// epilogue of the current one (cross-attention, S = 77, is a single K tile per item: without this it is launch-
+// and latency-bound).
+// Roles: warp 0 Q/K TMA loader | warp 1 QK^T issuer (one lane) | pass 2: warp 2 V loader, warp 3 PV issuer |
+//        softmax warps (8 in pass 1, 16 in pass 2; TMEM lane == row, so row reductions need no shuffles).
+// TMEM: S 2 x 128 columns + O 1-2 x dp columns.  P' goes through smem in the UMMA K-major 128B-swizzle
+// layout, written by the softmax threads.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -50,13 +49,12 @@ template <int PASS> struct AttCfg {
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 x 64] fp16 SW128 sub-tile
-constexpr int kMaxKvStages = 4;
 
 struct AttnDev {
   int b, heads, t, s, d, dp;
   int nkv, q_tiles, items;
   int nh;                       // 128-row query halves per work item (2: each K/V tile is loaded once for both)
-  int nq_buf, nk_buf, nv_buf, no_buf, pv_lag;
+  int nq_buf, nk_buf, nv_buf, no_buf;
   float alpha;  // scale * log2(e)
   int map_mode, real_time, start_peak;
   const float* delta;
@@ -728,7 +726,6 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   p.nk_buf = a->dp <= 64 ? 3 : 1;
   p.nv_buf = a->dp <= 64 ? 2 : 1;
   p.no_buf = a->dp <= 128 ? 2 : 1;
-  p.pv_lag = (p.nv_buf >= 2 && p.nk_buf >= 2) ? 2 : 1;   // PV issued this many steps behind QK^T
   p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
   p.alpha = a->scale * 1.4426950408889634f;
   p.map_mode = a->map_mode; p.real_time = a->real_time; p.start_peak = a->start_peak;

@@ -9,10 +9,11 @@
 // (quant/quant_layer.py:649-659) together with the residual / time-embedding adds that follow
 // (quant/quant_block.py:105-117, 165-186).
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM; 320 threads with the plain epilogue, 576 with the fused ones):
 //   warp 0      TMA producer   : A tile [128 x 64] and B tile [bn x 64] per stage, 128-byte swizzle
-//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128, N=bn, K=16) x 4 per stage
-//   warps 2..5  epilogue       : tcgen05.ld accumulator rows -> scale/bias/temb/resid -> fp16 stores
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128 | 256 as a CTA pair, N=bn, K=16) x 4 per stage
+//   warps 2..   epilogue       : tcgen05.ld accumulator rows -> scale/bias/temb/resid (+GEGLU | head split, +quantize)
+//                                -> shared-memory transpose -> coalesced stores (8 warps plain, 16 warps fused)
 // Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are visited n-fastest so concurrently resident CTAs share A and B
 // tiles through L2.
