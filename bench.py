@@ -216,6 +216,7 @@ def run_cuda(args):
     }
     line["cpu_baseline"] = cpu_baseline(torch, qnn, budget_s=float(os.environ.get("DGQ_CPU_BUDGET_S", "150"))) \
         if world == 1 and not args.no_cpu else None
+    line["torch_eager_b200_baseline"] = torch_eager_b200(torch, qnn, dev) if world == 1 and not args.no_cpu else None
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -348,6 +349,34 @@ def cpu_baseline(torch, qnn, budget_s):
     best = min(times)
     return {"value": round(1.0 / best, 5), "unit": "images/s", "cores": cores, "kind": "port",
             "sample": f"batch 1 of the same workload (one SDXL UNet call), best of {len(times)}, {best:.1f} s/call"}
+
+
+def torch_eager_b200(torch, qnn, dev):
+    """north_star: "the reference's PyTorch-on-B200 fake-quant path also listed" -- the oracle port (the
+    reference's fake-quant forward as plain PyTorch eager ops, fp32) executed on the B200 itself, batch 1 of the
+    same workload.  A baseline like cpu_baseline: never on the product path."""
+    try:
+        from oracle import dgq_oracle as O
+        sd, act, cfg = export_oracle_state(torch, qnn)
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        act = {k: v.to(dev) for k, v in act.items()}
+        inp = [x.to(dev) for x in make_inputs(torch, 1, seed=1000)]
+        added = {"text_embeds": inp[3], "time_ids": inp[4]}
+        times = []
+        with torch.no_grad():
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                O.unet_forward(MODEL, sd, act, cfg, inp[0], inp[1], inp[2], added)
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+        del sd, act
+        torch.cuda.empty_cache()
+        best = min(times[1:])
+        return {"value": round(1.0 / best, 4), "unit": "images/s", "kind": "port, torch eager fp32 on the same B200",
+                "sample": f"batch 1 (one SDXL UNet call), best of 2 after 1 warm-up, {best * 1e3:.0f} ms/call"}
+    except Exception as e:   # a baseline must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 def run_reference(args):

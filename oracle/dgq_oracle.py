@@ -291,7 +291,7 @@ def transformer2d(x, ctx, sd, act, name, cfg, *, n_layers: int, heads: int, line
 def timestep_embedding(t: Tensor, dim: int) -> Tensor:
     """Timesteps.forward (sd.py:25-39): cos first, then sin."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - 0.0)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - 0.0)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
