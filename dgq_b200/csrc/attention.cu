@@ -170,7 +170,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   constexpr int kSplit = PP ? 2 : Cfg::kSplit, kCh = PP ? 2 : Cfg::kCh;
   constexpr int kGroupThreads = PP ? kSoftmaxThreads / 2 : kSoftmaxThreads;   // threads sharing one score tile
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ base: the pointer keeps its address space, so the
+  // epilogue / softmax accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int dchunks = p.dp >> 6;
   const uint32_t q_bytes = dchunks * kChunkBytes;          // one Q tile / one K stage
   const uint32_t v_stage = 2 * p.dp * 128;                 // two [dp x 64] sub-tiles

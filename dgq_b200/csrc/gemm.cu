@@ -97,7 +97,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   constexpr int kEpiWarps = EpiCfg<kEpi>::kWarps;
   constexpr int kSplit = EpiCfg<kEpi>::kSplit;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET from the __shared__ base: the pointer keeps its address space, so the
+  // epilogue / softmax accesses compile to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
   float* s_epi = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
