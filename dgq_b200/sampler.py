@@ -172,7 +172,7 @@ class EulerAncestralSampler:
             ts = (np.arange(self.T, 0, -self.T / n)).round().copy().astype(np.float32) - 1
         else:
             raise ValueError(f"{self.spacing} is not supported. Please make sure to choose one of 'linspace', 'leading' or 'trailing'.")
-        sig = np.array(((1 - self.acp) / self.acp) ** 0.5)
+        sig = (((1 - self.acp) / self.acp) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32).astype(np.float64)
         self.timesteps = ts

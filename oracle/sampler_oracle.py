@@ -140,7 +140,7 @@ class EulerAncestralOracle:
             ts = (np.arange(self.T, 0, -self.T / n)).round().copy().astype(np.float32) - 1
         else:
             raise ValueError(self.spacing)
-        sig = np.array(((1 - self.acp) / self.acp) ** 0.5)
+        sig = (((1 - self.acp) / self.acp) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]).astype(np.float32))
         self.timesteps = torch.from_numpy(ts)
