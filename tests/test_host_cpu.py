@@ -205,3 +205,22 @@ def test_compiled_header_rejects_foreign_files(tmp_path):
     p.write_bytes(compiled.MAGIC + struct.pack("<Q", len(hj)) + hj)
     with pytest.raises(ValueError):
         compiled.read_header(str(p))
+
+
+def test_cli_accepts_the_reference_flags(monkeypatch):
+    """scripts/inference_qmodel.py takes every flag of the reference's src/inference_qmodel.py:17-44 (argument
+    names and types), so a command line written for the reference parses unchanged."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("inference_qmodel_cli", os.path.join(ROOT, "scripts", "inference_qmodel.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    argv = ["prog", "--use_group", "--num_inference_steps", "4", "--cali_ckpt", "x.pth", "--fp16", "--wq", "4", "--use_aq",
+            "--aq", "8", "--seed", "42", "--t2i_log_quant", "--t2i_real_time", "--t2i_start_peak", "--time_aware_aqtizer"]
+    monkeypatch.setattr("sys.argv", argv)
+    opt = cli.parse_args()
+    assert (opt.use_group, opt.num_inference_steps, opt.cali_ckpt, opt.fp16, opt.wq, opt.use_aq, opt.aq, opt.seed) == \
+           (True, 4, "x.pth", True, 4, True, 8, 42)
+    assert opt.t2i_log_quant and opt.t2i_real_time and opt.t2i_start_peak and opt.time_aware_aqtizer
+    monkeypatch.setattr("sys.argv", ["prog"])
+    d = cli.parse_args()       # the reference's defaults
+    assert (d.wq, d.aq, d.seed, d.num_inference_steps, d.use_aq, d.use_group) == (4, 8, 42, -1, False, False)
