@@ -773,8 +773,9 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
       break;
   }
   // every instantiation gets the maximum it can ever need once (227 KB opt-in)
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr;
+  int dev;
+  if (!attr.done(&dev)) {
     KernelFn all[] = {attention_kernel<1, 0, false, false>,
                       attention_kernel<2, DGQ_MAP_LOG2, true, false>, attention_kernel<2, DGQ_MAP_LOG2, true, true>,
                       attention_kernel<2, DGQ_MAP_LOG2, false, false>, attention_kernel<2, DGQ_MAP_LOG2, false, true>,
@@ -785,7 +786,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
       if (e != cudaSuccess) return static_cast<int>(e);
     }
-    attr_done = true;
+    attr.mark(dev);
   }
   if (smem2 > 232448) return DGQ_ERR_INVALID_VALUE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -22,6 +22,19 @@ namespace dgq {
 
 constexpr int kNumSMs = 148;
 
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) is per DEVICE: one flag word per call site, one bit
+// per device ordinal.  Racing host threads may both set the attribute (idempotent) before the bit is published.
+struct PerDeviceOnce {
+  unsigned long long mask = 0;
+  bool done(int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return (__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull;
+  }
+  void mark(int dev) { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+
 // quantize one value exactly as UniformAffineQuantizer does (quant/quant_layer.py:295-299):
 // IEEE division, round-half-to-even, clamp to [0, level-1].  Returns the integer code as float.
 __device__ __forceinline__ float uaq_code(float x, float delta, float zp, float qmax) {

@@ -652,12 +652,13 @@ static int pick_bn(int n, int step) {
 
 template <int kCtas, int kEpi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, cudaStream_t s) {
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static PerDeviceOnce attr;       // per instantiation, per device
+  int dev;
+  if (!attr.done(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmCfg<kCtas, kEpi>::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr.mark(dev);
   }
   const int tiles = p.m_tiles * p.n_tiles;
   constexpr int kGemmThreads = EpiCfg<kEpi>::kThreads;

@@ -870,15 +870,16 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
     // hot widths: tiled kernel (quantizer tables read once per CTA instead of once per row)
     const int tgrid = (m + kLnRows - 1) / kLnRows;
     const size_t smem = static_cast<size_t>(kLnRows) * c * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr;
+    int dev;
+    if (!attr.done(&dev)) {
       const int kMaxSmem = kLnRows * 1280 * 4;
       cudaError_t e = cudaFuncSetAttribute(ln_tile_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_tile_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_tile_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(ln_tile_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      attr_done = true;
+      attr.mark(dev);
     }
     if (norm) {
       DGQ_CHECK_ARG(gamma != nullptr && beta != nullptr);

@@ -47,13 +47,21 @@ def _pairs(act: dict) -> dict:
     return out
 
 
+def _is_disabled(named: dict, qpath: str) -> bool:
+    """quantizers that never run: conv_in / conv_out (disable_aq) and the log2 map quantizer's uniform twin"""
+    owner = named.get(qpath.rpartition(".")[0])
+    return bool(getattr(owner, "disable_aq", False))
+
+
 @torch.no_grad()
 def load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor] = None, use_aq: bool = False,
                     path: str = None, time_aware_aqtizer: bool = False, num_inference_steps: int = 25,
                     use_group: bool = False) -> None:
     logger.info("Loading calibration model...")
     full = torch.load(path, map_location="cpu") if isinstance(path, str) else path
-    ckpt = dict(full["weight"]) if "weight" in full else dict(full)
+    # an un-merged activation file ({'act_0': ..}, reference calibration_group_quantization.py:102-107) carries no
+    # weights: the reference then loads nothing into the model (strict=False) and keeps the pipe's own weights
+    ckpt = dict(full["weight"]) if "weight" in full else {k: v for k, v in full.items() if not k.startswith("act_")}
     dev = qnn.device
 
     # weight quantizers: what the first dummy forward initialises (reference :224-225, quant_layer :253-264)
@@ -78,7 +86,7 @@ def load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor] = None, use_
 
     if use_aq:
         qnn.set_quant_state(use_wq=True, use_aq=True)
-        tables = _act_tables(full) if "weight" in full else []
+        tables = _act_tables(full)       # act_k are read from the raw file whether or not it is merged (:294, :311)
         if time_aware_aqtizer:
             if not tables:
                 raise KeyError("act_0")
@@ -100,4 +108,12 @@ def load_cali_model(qnn: QuantModel, init_data: Tuple[torch.Tensor] = None, use_
                 if isinstance(qt, UniformAffineQuantizer):
                     qt.zero_point = nn.Parameter(z.to(dev))
                 qt.init = True
+            # The reference initialises quantizers that the checkpoint does not cover from its RANDOM dummy
+            # forward (:255-257) -- values that mean nothing.  Here that is an error, named at load time.
+            missing = [p for p, m in named.items()
+                       if isinstance(m, UniformAffineQuantizer) and ".aqtizer" in p and m.delta is None
+                       and not _is_disabled(named, p)]
+            if missing:
+                raise KeyError(f"activation checkpoint has no (delta, zero_point) for {len(missing)} quantizers, "
+                               f"e.g. {missing[:4]}")
     logger.info("Loading calibration model done.")
