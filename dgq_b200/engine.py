@@ -412,6 +412,9 @@ def cross_kv_prefetch(unet, ctx: torch.Tensor) -> dict:
             ev = torch.cuda.Event()
             ev.record(side)
             out[id(a2)] = (dk, dv, ev)
+    if cx.data_ptr() != ctx.data_ptr():
+        cx.record_stream(side)            # a converted copy (bf16 / strided ctx) allocated on the calling stream
+    out["_ctx_operand"] = cx              # ... and kept alive until the last attn2 has joined
     return out
 
 

@@ -53,6 +53,7 @@ class QuantModel(nn.Module):
         self._step_tables: Optional[List[Dict[str, object]]] = None
         self._num_inference_steps = None
         self._graphs = {}
+        self._graph_pool = None
         self._use_graphs = False
 
     # -- tree surgery (reference :66-103) ---------------------------------------------------
@@ -186,8 +187,13 @@ class QuantModel(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             n0 = ops.LAUNCHES
+            # ONE memory pool for every (step, shape) graph of this model: time-aware sampling captures a
+            # graph per denoising step (25-50 for SD PLMS) and the graphs replay strictly one after another,
+            # so they can share their working set instead of each pinning a private copy of it
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, pool=self._graph_pool):
                 out = call()
             ent = {"graph": graph, "st": st, "out": out, "launches": ops.LAUNCHES - n0}
             self._graphs[key] = ent
@@ -201,6 +207,8 @@ class QuantModel(nn.Module):
         ent["graph"].replay()
         from .. import ops
         ops.LAUNCHES += ent["launches"]
+        # the result aliases the graph's static output buffer: it is valid until the next replay of THIS entry
+        # (the samplers consume it in their step kernel before the next UNet call); clone it to keep it longer
         return [ent["out"][0]]
 
     def half(self):
