@@ -354,6 +354,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const size_t ooff = orow_idx * p.ldo + head * p.d;
           __half* orow = static_cast<__half*>(p.out) + ooff;
           float* orow32 = static_cast<float*>(p.out) + ooff;
+          uint8_t* orow8 = static_cast<uint8_t*>(p.out) + ooff;
+          const bool out_u8 = p.oq_emit_int == 2;   // u8 codes for a kind::i8 to_out GEMM (ldo in bytes)
           float rd = 1.f, rz = 0.f, ri = 1.f;       // row-indexed / scalar output quantizer
           if (rok && (p.oq_mode == DGQ_Q_SCALAR || p.oq_mode == DGQ_Q_ROWWISE)) {
             const int jq = p.oq_mode == DGQ_Q_ROWWISE ? static_cast<int>(orow_idx % p.oq_period) : 0;
@@ -393,6 +395,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 } else if (p.oq_mode != DGQ_Q_NONE) {
                   if (p.oq_emit_int) uaq_lean1_lh<true, 8>(f, rd, ri, -rz, __fsub_rn(p.oq_qmax, rz));
                   else uaq_lean1_lh<false, 8>(f, rd, ri, -rz, __fsub_rn(p.oq_qmax, rz));
+                  if (out_u8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] += rz;          // the u8 code itself, exact in fp16
+                  }
                 }
               }
               if (stage == nullptr) {
@@ -400,6 +406,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                   if (p.out_is_f32) {
                     *reinterpret_cast<float4*>(orow32 + d0) = make_float4(f[0], f[1], f[2], f[3]);
                     *reinterpret_cast<float4*>(orow32 + d0 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+                  } else if (out_u8) {
+                    const uint4 h = pack8(f);
+                    *reinterpret_cast<uint2*>(orow8 + d0) = make_uint2(halves4_to_u8(h.x, h.y), halves4_to_u8(h.z, h.w));
                   } else {
                     *reinterpret_cast<uint4*>(orow + d0) = pack8(f);
                   }
@@ -435,8 +444,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                   const int rr = i * 8 + (lane >> 2), ch = lane & 3;
                   const uint4 x = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
                   const int col = cb + ch * 8;
-                  if (rr < rows_ok && col < c_hi && col < p.d)
-                    *reinterpret_cast<uint4*>(orow + row0 + static_cast<ptrdiff_t>(rr) * p.ldo + col) = x;
+                  if (rr < rows_ok && col < c_hi && col < p.d) {
+                    if (out_u8)
+                      *reinterpret_cast<uint2*>(orow8 + row0 + static_cast<ptrdiff_t>(rr) * p.ldo + col) =
+                          make_uint2(halves4_to_u8(x.x, x.y), halves4_to_u8(x.z, x.w));
+                    else
+                      *reinterpret_cast<uint4*>(orow + row0 + static_cast<ptrdiff_t>(rr) * p.ldo + col) = x;
+                  }
                 }
               }
               __syncwarp();
@@ -714,6 +728,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   DGQ_CHECK_ARG(a->out_q.mode >= DGQ_Q_NONE && a->out_q.mode <= DGQ_Q_ROWWISE);
   DGQ_CHECK_ARG(a->out_q.mode == DGQ_Q_NONE || (a->out_q.delta != nullptr && a->out_q.zp != nullptr));
   DGQ_CHECK_ARG(!(a->out_q.emit_int && a->out_q.mode == DGQ_Q_KWISE));
+  DGQ_CHECK_ARG(a->out_q.emit_int != 2 || (a->out_q.mode != DGQ_Q_NONE && !a->out_is_f32 && a->ldo % 16 == 0));
 
   AttnDev p;
   p.b = a->b; p.heads = a->heads; p.t = a->t; p.s = a->s; p.d = a->d; p.dp = a->dp;

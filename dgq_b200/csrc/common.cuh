@@ -237,6 +237,13 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
   v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+// fp16 pairs holding integers 0..255 -> their low bytes: h + 1024 = 0x6400 | value (exact), one PRMT gathers them
+__device__ __forceinline__ uint32_t halves4_to_u8(uint32_t h01, uint32_t h23) {
+  const __half2 k = __half2half2(__ushort_as_half(0x6400));
+  const __half2 a = __hadd2(*reinterpret_cast<const __half2*>(&h01), k);
+  const __half2 b = __hadd2(*reinterpret_cast<const __half2*>(&h23), k);
+  return __byte_perm(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b), 0x6420);
+}
 __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   Half8 t;
 #pragma unroll

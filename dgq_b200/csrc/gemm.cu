@@ -17,6 +17,15 @@
 // Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are visited n-fastest so concurrently resident CTAs share A and B
 // tiles through L2.
+//
+// kI8 (dgq_gemm_i8): the same pipeline on tcgen05.mma kind::i8 -- 2x the MMA rate (profiles/r2_probes.txt) -- for
+// layers whose activation scale is constant along K (scalar / row-wise: every layer of the g=1 configs).
+//   A = u8 activation codes, B = s8 (weight code - b_off[n]), s32 accumulate:
+//   sum_k (c_mk - za_m)(w_nk - wz_n) = acc - za_m * colsum_n + e_n * (rowsum_m - K za_m),  e_n = b_off_n - wz_n
+//   evaluated in INTEGER arithmetic in the epilogue (exact), then * delta_a[m] * delta_w[n] + bias as before.
+//   colsum_n = sum_k B[n,k] is a pack-time table; rowsum_m = sum_k c_mk is needed only when e_n != 0 (W8: the
+//   8-bit weight codes minus their zero point do not fit s8) and is computed in the kernel by 4 extra warps that
+//   read each A stage from shared memory (dp4a), so no producer has to emit it.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,18 +34,19 @@
 namespace dgq {
 
 constexpr int kBM = 128;           // rows of A per CTA
-constexpr int kBK = 64;
+constexpr int kBK = 64;            // K elements per stage for fp16 operands (128 bytes); 128 for the u8 / s8 operands
 constexpr int kMaxBN = 256;
 // warp 0 TMA, warp 1 MMA, then the epilogue warps: 8 for the plain epilogue (2 column splits per TMEM
 // lane quarter), 16 for the fused GEGLU / QKV epilogues (4 splits) -- those run ~40 dependent ALU
 // instructions per result, so with 2 warps per scheduler they, not the MMAs, bounded the tile time
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kStgLd = 36;                         // padded row stride (floats) of the fp32 epilogue transpose buffer
-constexpr int kEpiTab = 6;                         // per-column tables staged per tile
+constexpr int kEpiTab = 8;                         // per-column tables staged per tile
+constexpr int kRsRing = 8;                         // kI8: ring of per-tile row-sum vectors (row-sum warps run ahead)
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
-template <int kEpi> struct EpiCfg {
+template <int kEpi, bool kI8 = false> struct EpiCfg {
   static constexpr int kWarps = kEpi == EPI_PLAIN ? 8 : 16;
-  static constexpr int kThreads = 64 + 32 * kWarps;
+  static constexpr int kThreads = 64 + 32 * kWarps + (kI8 ? 32 : 0);   // kI8: + the row-sum warp
   static constexpr int kSplit = kWarps / 4;        // column splits of a tile (one per warp of a lane quarter)
   // per-warp transpose buffer: [32 rows][36] fp32 (plain), [32 rows][32] fp16 with a 16-byte XOR swizzle (fused)
   static constexpr uint32_t kStgBytes = kEpi == EPI_PLAIN ? 32 * kStgLd * 4 : 32 * 32 * 2;
@@ -50,14 +60,15 @@ struct EpiQuant {   // quantizer applied by the fused epilogues (the NEXT op's a
   int emit_int;
 };
 
-template <int kCtas, int kEpi> struct GemmCfg {
+template <int kCtas, int kEpi, bool kI8 = false> struct GemmCfg {
   static constexpr int kStages = kCtas == 1 ? 3 : 5;
   static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // [2 buffers][scale | bias | q.delta | 1/q.delta | -q.zp | qmax - q.zp][256] fp32 + one [32 rows][36] fp32 transpose
   // buffer per epilogue warp
   static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + EpiCfg<kEpi>::kWarps * EpiCfg<kEpi>::kStgBytes;
-  static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t kRsBytes = kI8 ? kRsRing * kBM * 4 : 0;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + kRsBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 struct GemmDev {
@@ -78,6 +89,10 @@ struct GemmDev {
   EpiQuant q2;
   // EPI_QKV geometry: GEMM row = (batch, token), column = (head, channel)
   int heads, d, dp, tokens, tp, transpose, skip_first;
+  // kI8
+  const int32_t* colsum;   // [n] sum_k B[n, k]
+  const int32_t* b_off;    // [n] e_n = b_off_n - wz_n, or nullptr (= 0: the weight zero point is folded into B)
+  const float* row_zp;     // activation zero point: row_zp[m % row_period]
 };
 
 template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
@@ -88,11 +103,12 @@ template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the
 // 256 x bn tile -- each CTA stages its own 128 rows of A and bn/2 rows of B, the leader issues the
 // MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
 // L2->smem bytes of the single-CTA tile.
-template <int kCtas, int kEpi>
-__global__ void __launch_bounds__(EpiCfg<kEpi>::kThreads, 1)
+template <int kCtas, int kEpi, bool kI8>
+__global__ void __launch_bounds__(EpiCfg<kEpi, kI8>::kThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
-  using Cfg = GemmCfg<kCtas, kEpi>;
+  using Cfg = GemmCfg<kCtas, kEpi, kI8>;
+  constexpr int kBKe = kI8 ? 2 * kBK : kBK;      // K elements per 128-byte stage row
   constexpr int kStages = Cfg::kStages;
   constexpr int kEpiWarps = EpiCfg<kEpi>::kWarps;
   constexpr int kSplit = EpiCfg<kEpi>::kSplit;
@@ -107,14 +123,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained (leader's copy is the one used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* mdone_bar = tempty_bar + 2;        // [kStages] kI8 pairs: the MMAs reading this stage have retired
+  uint64_t* rfull_bar = mdone_bar + kStages;   // [kRsRing] kI8: row sums of a tile published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull_bar + kRsRing);
+  int* s_rowsum = reinterpret_cast<int*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes + 512);   // [kRsRing][128]
+  const bool need_rowsum = kI8 && p.b_off != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
   const int worker = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int workers = static_cast<int>(gridDim.x) / kCtas;
-  const int k_blocks = (p.k + kBK - 1) / kBK;
+  const int k_blocks = (p.k + kBKe - 1) / kBKe;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int b_rows = p.bn / kCtas;             // rows of B staged by this CTA
 
@@ -123,8 +143,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     prefetch_tmap(&tmap_b);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], need_rowsum ? 2 : 1);   // MMA commit (+ the row-sum warp)
+      mbar_init(&mdone_bar[i], 1);
     }
+    for (int i = 0; i < kRsRing; ++i) mbar_init(&rfull_bar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps * kCtas);
@@ -153,12 +175,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kCtas == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
-            tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, row_a);
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, row_b);
+            tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBKe, row_a);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBKe, row_b);
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
-            tma_load_2d_pair(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, row_a);
-            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, row_b);
+            tma_load_2d_pair(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBKe, row_a);
+            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBKe, row_b);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -167,7 +189,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM * kCtas, p.bn);
+      const uint32_t idesc = kI8 ? umma_idesc_i8(kBM * kCtas, p.bn, false, true) : umma_idesc_f16(kBM * kCtas, p.bn);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = worker; tile < total_tiles; tile += workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -180,16 +202,58 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int ks = 0; ks < kBK / 16; ++ks) {
-            // advancing 16 halves (32 B) along K inside the swizzle atom: +2 in the >>4 address field
-            if (kCtas == 2) tc_mma_f16_pair(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
-            else tc_mma_f16(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+            // advancing 16 halves / 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
+            if (kI8) {
+              if (kCtas == 2) tc_mma_i8_pair(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+              else tc_mma_i8(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+            } else {
+              if (kCtas == 2) tc_mma_f16_pair(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+              else tc_mma_f16(d_tmem, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0 ? 1u : 0u);
+            }
           }
           // frees the smem stage (in both CTAs) once these MMAs retire
           if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+          if (kI8 && kCtas == 2 && need_rowsum) tc_commit_pair(&mdone_bar[stage]);   // the row-sum warps' cue
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (kCtas == 2) tc_commit_pair(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);  // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (kI8 && warp >= 2 + kEpiWarps) {
+    // ------------------------------------------------------------ row sums of the u8 A tile (kI8, W8 weights only)
+    // one warp; lane l owns rows l, l + 32, l + 64, l + 96 of this CTA's 128 x 128-byte A stage.  The 16-byte chunks
+    // of a row are read in the rotated order (i + row) & 7 -- any order sums the same, and the 8 lanes of a
+    // quarter-warp then touch 8 different bank groups
+    if (need_rowsum) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = worker; tile < total_tiles; tile += workers, ++it) {
+        uint32_t sum[4] = {0u, 0u, 0u, 0u};
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          // single CTA: as soon as the stage has landed; pair: the transaction bytes are counted on the LEADER's
+          // barrier only, so both CTAs take the multicast "MMAs of this stage retired" commit as their cue
+          if (kCtas == 1) mbar_wait(&full_bar[stage], phase); else mbar_wait(&mdone_bar[stage], phase);
+          const uint8_t* base = smem_a + stage * kABytes + lane * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 w = *reinterpret_cast<const uint4*>(base + q * 4096 + (((i + lane) & 7) << 4));
+              sum[q] = __dp4a(w.x, 0x01010101u, sum[q]);
+              sum[q] = __dp4a(w.y, 0x01010101u, sum[q]);
+              sum[q] = __dp4a(w.z, 0x01010101u, sum[q]);
+              sum[q] = __dp4a(w.w, 0x01010101u, sum[q]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        // ring of kRsRing tiles: this warp can be at most 2 + kStages tiles ahead of the epilogue
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_rowsum[(it % kRsRing) * kBM + q * 32 + lane] = static_cast<int>(sum[q]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rfull_bar[it % kRsRing]);
       }
     }
   } else {
@@ -230,9 +294,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       float* s_qi = s_qd + kMaxBN;
       float* s_qz = s_qi + kMaxBN;      // PLAIN-era name: holds lo = -zp (the fused epilogues clamp code - zp to [lo, hi])
       float* s_qh = s_qz + kMaxBN;      // hi = qmax - zp
+      int* s_cs = reinterpret_cast<int*>(s_qh + kMaxBN);   // kI8: colsum_n
+      int* s_eo = s_cs + kMaxBN;                            // kI8: e_n
       for (int j = etid; j < p.bn; j += 32 * kEpiWarps) {
         const int n = ncol0 + j;
         float sc = 1.0f, bi = 0.0f;
+        if (kI8) {
+          s_cs[j] = n < p.n ? __ldg(p.colsum + n) : 0;
+          s_eo[j] = (n < p.n && p.b_off != nullptr) ? __ldg(p.b_off + n) : 0;
+        }
         if (n < p.n) {
           if (p.scale != nullptr) sc = __ldg(p.scale + n);
           if (p.bias != nullptr) bi = __ldg(p.bias + n);
@@ -265,6 +335,22 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                  ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
                                  : nullptr;
       const float rs = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
+      // kI8: integer correction terms of this thread's row: -za and (rowsum - K * za)
+      int nrz = 0, rsp = 0;
+      if (kI8) {
+        const int za = row_ok ? static_cast<int>(__ldg(p.row_zp + (row % p.row_period))) : 0;
+        nrz = -za;
+        if (need_rowsum) {
+          mbar_wait(&rfull_bar[it % kRsRing], (it / kRsRing) & 1);
+          rsp = s_rowsum[(it % kRsRing) * kBM + quad * 32 + lane] - p.k * za;
+        }
+      }
+      // accumulator word j (tile column) -> float: kind::f16 holds fp32; kind::i8 holds s32 and the zero-point
+      // corrections are applied in exact integer arithmetic first
+      auto accf = [&](uint32_t raw, int j) -> float {
+        if (kI8) return __int2float_rn(static_cast<int>(raw) + nrz * s_cs[j] + s_eo[j] * rsp);
+        return __uint_as_float(raw);
+      };
       // fused quantizer, row-indexed parameters (thread = row)
       float qd_row = 1.0f, qi_row = 1.0f, qz_row = 0.0f;
       bool q_on = kEpi != EPI_PLAIN && q2.mode != DGQ_Q_NONE;
@@ -289,10 +375,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int v = 0; v < 8; ++v) {
           const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
           const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
-          g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
-          g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
-          g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
-          g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+          g[v * 4 + 0] = fmaf(accf(r[v * 4 + 0], j0 + v * 4 + 0) * rs, sc.x, bi.x);
+          g[v * 4 + 1] = fmaf(accf(r[v * 4 + 1], j0 + v * 4 + 1) * rs, sc.y, bi.y);
+          g[v * 4 + 2] = fmaf(accf(r[v * 4 + 2], j0 + v * 4 + 2) * rs, sc.z, bi.z);
+          g[v * 4 + 3] = fmaf(accf(r[v * 4 + 3], j0 + v * 4 + 3) * rs, sc.w, bi.w);
         }
       };
       if constexpr (kEpi != EPI_PLAIN) {
@@ -305,11 +391,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           for (int v = 0; v < 4; ++v) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
             const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
-            if (has_rs) {
-              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]) * rs, sc.x, bi.x);
-              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]) * rs, sc.y, bi.y);
-              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]) * rs, sc.z, bi.z);
-              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]) * rs, sc.w, bi.w);
+            if (has_rs || kI8) {
+              g[v * 4 + 0] = fmaf(accf(r[v * 4 + 0], j0 + v * 4 + 0) * rs, sc.x, bi.x);
+              g[v * 4 + 1] = fmaf(accf(r[v * 4 + 1], j0 + v * 4 + 1) * rs, sc.y, bi.y);
+              g[v * 4 + 2] = fmaf(accf(r[v * 4 + 2], j0 + v * 4 + 2) * rs, sc.z, bi.z);
+              g[v * 4 + 3] = fmaf(accf(r[v * 4 + 3], j0 + v * 4 + 3) * rs, sc.w, bi.w);
             } else {
               g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]), sc.x, bi.x);
               g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]), sc.y, bi.y);
@@ -319,11 +405,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           }
         };
         const float lo_row = -qz_row, hi_row = __fsub_rn(q2.qmax, qz_row);
+        const bool out_u8 = kEpi == EPI_GEGLU && q2.emit_int == 2;   // the operand of a kind::i8 consumer: u8 codes
         auto fused_quant16 = [&](float (&g)[16], int slot0) {
           if (!q_on || q_skip) return;
           if (q2.mode == DGQ_Q_ROWWISE) {
             if (q2.emit_int) uaq_lean1_lh<true, 16>(g, qd_row, qi_row, lo_row, hi_row);
             else uaq_lean1_lh<false, 16>(g, qd_row, qi_row, lo_row, hi_row);
+            if (out_u8) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] += qz_row;          // (code - zp) + zp: the code, exact in fp16
+            }
             return;
           }
 #pragma unroll
@@ -345,7 +436,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (q2.emit_int) uaq_lean_lh<true, 8>(x, dd, ii, lo, hi);
             else uaq_lean_lh<false, 8>(x, dd, ii, lo, hi);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[v * 8 + i] = x[i];
+            for (int i = 0; i < 8; ++i) g[v * 8 + i] = out_u8 ? x[i] - lo[i] : x[i];   // lo = -zp
           }
         };
         const uint32_t t_acc = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -432,7 +523,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const int rl = rr * 4 + rl0;
                 if (warp_row0 + rl < p.m) {
                   const uint2 x = *reinterpret_cast<const uint2*>(stg8 + rl * 64 + ((ch ^ ((rl >> 1) & 3)) << 4) + sub);
-                  *reinterpret_cast<uint2*>(p.out + o) = x;
+                  if (out_u8) *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p.out) + o) = halves4_to_u8(x.x, x.y);
+                  else *reinterpret_cast<uint2*>(p.out + o) = x;
                 }
                 o += row_step;
                 if (kEpi == EPI_QKV) {
@@ -499,7 +591,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           if (has_resid && c + 1 < c_end) ldres(c + 1, t_nxt);
           tc_wait_ld();
           float g[32];
-          if (has_rs) {
+          if (has_rs || kI8) {
             affine32(r, j0, g);
           } else {
 #pragma unroll
@@ -622,16 +714,18 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// fp16 row-major [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
+// row-major [rows, cols] with row stride ld (elements) of fp16 (esize 2) or u8 / s8 (esize 1);
+// box = [box_rows, 128 bytes of columns], 128B swizzle
 int make_tmap_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                 uint32_t box_rows) {
+                 uint32_t box_rows, int esize = 2) {
   EncodeTiledFn enc = get_encode_tiled();
   if (enc == nullptr) return static_cast<int>(cudaErrorNotSupported);
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  cuuint64_t gstride[1] = {ld * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esize), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                   const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
@@ -650,27 +744,27 @@ static int pick_bn(int n, int step) {
   return best;
 }
 
-template <int kCtas, int kEpi>
+template <int kCtas, int kEpi, bool kI8>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, cudaStream_t s) {
   static PerDeviceOnce attr;       // per instantiation, per device
   int dev;
   if (!attr.done(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<kCtas, kEpi>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi, kI8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<kCtas, kEpi, kI8>::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr.mark(dev);
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  constexpr int kGemmThreads = EpiCfg<kEpi>::kThreads;
+  constexpr int kGemmThreads = EpiCfg<kEpi, kI8>::kThreads;
   if (kCtas == 1) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_f16_kernel<kCtas, kEpi><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi>::kSmem, s>>>(ta, tb, p);
+    gemm_f16_kernel<kCtas, kEpi, kI8><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi, kI8>::kSmem, s>>>(ta, tb, p);
   } else {
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = GemmCfg<kCtas, kEpi>::kSmem;
+    cfg.dynamicSmemBytes = GemmCfg<kCtas, kEpi, kI8>::kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -679,7 +773,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtas, kEpi>, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtas, kEpi, kI8>, ta, tb, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   DGQ_RETURN_LAST_ERROR();
@@ -687,11 +781,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
 
 }  // namespace dgq
 
-extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
+static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
   using namespace dgq;
   DGQ_CHECK_ARG(a != nullptr && a->a != nullptr && a->b != nullptr);
   DGQ_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0);
   DGQ_CHECK_ARG(a->k % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->n % 8 == 0 && a->ldc % 8 == 0);
+  if (i8) {   // byte operands: 16-byte aligned rows; zero-point corrections need their tables
+    DGQ_CHECK_ARG(a->k % 16 == 0 && a->lda % 16 == 0 && a->ldb % 16 == 0);
+    DGQ_CHECK_ARG(a->colsum != nullptr && a->row_zp != nullptr && a->row_scale != nullptr);
+  }
   DGQ_CHECK_ARG(a->out != nullptr || a->out_f32 != nullptr);
   DGQ_CHECK_ARG(a->temb == nullptr || (a->rows_per_batch > 0 && a->ld_temb % 8 == 0));
   DGQ_CHECK_ARG(a->resid == nullptr || a->ld_resid % 8 == 0);
@@ -702,7 +800,8 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
     DGQ_CHECK_ARG(q.mode >= DGQ_Q_NONE && q.mode <= DGQ_Q_ROWWISE);
     DGQ_CHECK_ARG(q.mode == DGQ_Q_NONE || (q.delta != nullptr && q.zp != nullptr));
     DGQ_CHECK_ARG(q.mode != DGQ_Q_ROWWISE || q.period > 0);
-    DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE));
+    DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE) && q.emit_int >= 0 && q.emit_int <= 2);
+    DGQ_CHECK_ARG(q.emit_int != 2 || (a->epi == DGQ_EPI_GEGLU && q.mode != DGQ_Q_NONE));
   }
   if (a->epi == DGQ_EPI_GEGLU) DGQ_CHECK_ARG(a->n % 64 == 0 && a->ldc >= a->n / 2 && static_cast<int64_t>(a->m) * a->ldc < (int64_t(1) << 31));
   if (a->epi == DGQ_EPI_QKV) {
@@ -743,21 +842,36 @@ extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) {
   p.q2 = EpiQuant{a->q2.delta, a->q2.zp, a->q2.mode, a->q2.period > 0 ? a->q2.period : 1, a->q2.qmax, a->q2.emit_int};
   p.heads = a->heads; p.d = a->d > 0 ? a->d : 1; p.dp = a->dp; p.tokens = a->tokens > 0 ? a->tokens : 1;
   p.tp = a->tp; p.transpose = a->transpose; p.skip_first = a->skip_first;
+  p.colsum = i8 ? a->colsum : nullptr; p.b_off = i8 ? a->b_off : nullptr; p.row_zp = i8 ? a->row_zp : nullptr;
 
   CUtensorMap ta, tb;
-  int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM);
+  const int esize = i8 ? 1 : 2;
+  int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM, esize);
   if (rc != 0) return rc;
   // B rows beyond n are zero-filled by TMA (out-of-bounds box rows)
-  rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn / ctas);
+  rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn / ctas, esize);
   if (rc != 0) return rc;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (ctas == 1) {
-    if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU>(ta, tb, p, s);
-    if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV>(ta, tb, p, s);
-    return launch_gemm<1, EPI_PLAIN>(ta, tb, p, s);
+  if (i8) {
+    if (ctas == 1) {
+      if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU, true>(ta, tb, p, s);
+      if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV, true>(ta, tb, p, s);
+      return launch_gemm<1, EPI_PLAIN, true>(ta, tb, p, s);
+    }
+    if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<2, EPI_GEGLU, true>(ta, tb, p, s);
+    if (a->epi == DGQ_EPI_QKV) return launch_gemm<2, EPI_QKV, true>(ta, tb, p, s);
+    return launch_gemm<2, EPI_PLAIN, true>(ta, tb, p, s);
   }
-  if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<2, EPI_GEGLU>(ta, tb, p, s);
-  if (a->epi == DGQ_EPI_QKV) return launch_gemm<2, EPI_QKV>(ta, tb, p, s);
-  return launch_gemm<2, EPI_PLAIN>(ta, tb, p, s);
+  if (ctas == 1) {
+    if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU, false>(ta, tb, p, s);
+    if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV, false>(ta, tb, p, s);
+    return launch_gemm<1, EPI_PLAIN, false>(ta, tb, p, s);
+  }
+  if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<2, EPI_GEGLU, false>(ta, tb, p, s);
+  if (a->epi == DGQ_EPI_QKV) return launch_gemm<2, EPI_QKV, false>(ta, tb, p, s);
+  return launch_gemm<2, EPI_PLAIN, false>(ta, tb, p, s);
 }
+
+extern "C" int dgq_gemm_f16(const dgq_gemm_t* a, void* stream) { return gemm_dispatch(a, stream, false); }
+extern "C" int dgq_gemm_i8(const dgq_gemm_t* a, void* stream) { return gemm_dispatch(a, stream, true); }

@@ -29,6 +29,25 @@ static QuantDev to_dev(const dgq_quant_t& q) {
   return QuantDev{q.delta, q.zp, q.inv_delta, q.mode, q.period, q.qmax, q.emit_int};
 }
 
+// zero point of row `row` for the SCALAR / ROWWISE quantizers (the u8-code output adds it back)
+__device__ __forceinline__ float quant_zp(const QuantDev& q, int row) {
+  if (q.mode == DGQ_Q_SCALAR) return __ldg(q.zp);
+  if (q.mode == DGQ_Q_ROWWISE) return __ldg(q.zp + row % q.period);
+  return 0.0f;
+}
+// store 8 consecutive operand values of one row at element index `idx`: fp16 (16 bytes), or -- emit_int == 2 -- the
+// u8 codes (8 bytes) of the kind::i8 GEMM, rebuilt from the integer (code - zp) the quantizer returned
+__device__ __forceinline__ void store8(void* out, size_t idx, const float (&v)[8], int emit_int, float zp) {
+  if (emit_int == 2) {
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i >> 2] |= static_cast<uint32_t>(__float2int_rn(v[i] + zp)) << (8 * (i & 3));
+    *reinterpret_cast<uint2*>(static_cast<uint8_t*>(out) + idx) = make_uint2(w[0], w[1]);
+  } else {
+    *reinterpret_cast<uint4*>(static_cast<__half*>(out) + idx) = pack8(v);
+  }
+}
+
 // quantize 8 consecutive K positions k0..k0+7 of row `row` in place (no code output): the lean path
 // of every fused producer.  KWISE reads (delta, 1/delta, zp) vectors, SCALAR / ROWWISE one triple.
 __device__ __forceinline__ void quant8_lean(const QuantDev& q, float (&v)[8], int k0, int row) {
@@ -122,9 +141,10 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(idx / kvec);
     const int k0 = static_cast<int>(idx % kvec) << 3;
-    __half* dst = p.out + static_cast<size_t>(m) * p.ldo + k0;
+    const size_t dst = static_cast<size_t>(m) * p.ldo + k0;
     if (k0 >= K) {  // zero padding of the K tail (ldo > K)
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      if (p.q.emit_int == 2) *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.out) + dst) = make_uint2(0, 0);
+      else *reinterpret_cast<uint4*>(p.out + dst) = make_uint4(0, 0, 0, 0);
       continue;
     }
     const int tap = k0 / C, c = k0 % C;
@@ -159,7 +179,8 @@ __global__ void __launch_bounds__(256) act_producer_kernel(const ProducerDev p) 
     uint8_t* cdst = p.codes != nullptr ? p.codes + static_cast<size_t>(m) * K + k0 : nullptr;
     if (inside || p.pad_quantized) quant8(p.q, v, k0, m, cdst);
     else if (cdst != nullptr) *reinterpret_cast<uint2*>(cdst) = make_uint2(0, 0);
-    *reinterpret_cast<uint4*>(dst) = pack8(v);
+    // an un-quantized padding tap is an exact 0 = (code - zp) 0, i.e. the code zp in the u8 operand
+    store8(p.out, dst, v, p.q.emit_int, p.q.emit_int == 2 ? quant_zp(p.q, m) : 0.0f);
   }
 }
 
@@ -278,6 +299,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
       const float4 a1 = *reinterpret_cast<const float4*>(&patch[pp][(kTileC / 2) + (cg >> 1)]);
       v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
       const bool quantize = QMODE != DGQ_Q_NONE && (inside[pp] || p.pad_quantized);
+      float zrow = 0.f;                   // zero point of this row, for the u8-code output
       if (kCodes) {
         if (QMODE == DGQ_Q_ROWWISE) {
           const int j = m % q.period;
@@ -296,6 +318,7 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
             else hi |= static_cast<uint32_t>(cd[i]) << (8 * (i - 4));
           }
         }
+        zrow = z[0];
         *reinterpret_cast<uint2*>(p.codes + static_cast<size_t>(m) * (KS * KS * C) + k0) = make_uint2(lo, hi);
       } else if (quantize) {
         if (QMODE == DGQ_Q_KWISE) {
@@ -307,11 +330,16 @@ __global__ void __launch_bounds__(256) conv_producer_kernel(const ProducerDev p,
             dd = __ldg(q.delta + j); zz = __ldg(q.zp + j);
             ii = q.inv != nullptr ? __ldg(q.inv + j) : rcp_rn_slow(dd);
           }
+          zrow = zz;
           if (emit_int) uaq_lean1_lh<true, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
           else uaq_lean1_lh<false, 8>(v, dd, ii, -zz, __fsub_rn(q.qmax, zz));
         }
+      } else if (QMODE == DGQ_Q_SCALAR) {
+        zrow = z[0];                      // padding tap left at exact 0: the u8 operand stores the code zp
+      } else if (QMODE == DGQ_Q_ROWWISE && q.emit_int == 2) {
+        zrow = __ldg(q.zp + m % q.period);
       }
-      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(m) * p.ldo + k0) = pack8(v);
+      store8(p.out, static_cast<size_t>(m) * p.ldo + k0, v, q.emit_int, zrow);
     }
   }
 }
@@ -474,6 +502,7 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
   for (int o = 0; o < rq.n_out; ++o) {
     const QuantDev q = rq.q[o];
     __half* orow = rq.out[o] + static_cast<size_t>(warp) * c;
+    const float zrow = q.emit_int == 2 ? quant_zp(q, warp) : 0.0f;
     if (rq.codes[o] == nullptr) {
 #pragma unroll
       for (int j = 0; j < kMaxVecPerLane; ++j) {
@@ -483,7 +512,7 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) t[i] = v[j][i];
           quant8_lean(q, t, cv << 3, warp);
-          *reinterpret_cast<uint4*>(orow + (cv << 3)) = pack8(t);
+          store8(rq.out[o], static_cast<size_t>(warp) * c + (cv << 3), t, q.emit_int, zrow);
         }
       }
     } else {
@@ -498,6 +527,26 @@ __global__ void __launch_bounds__(256) row_quant_kernel(const TIn* __restrict__ 
           *reinterpret_cast<uint4*>(orow + (cv << 3)) = pack8(t);
         }
       }
+    }
+  }
+}
+
+// rows wider than the register-cached kernel supports (ff.net.2 inputs, c = 5120, when they do not come from the
+// fused GEGLU epilogue): quantizer only, streamed -- one warp per row, nothing cached
+template <typename TIn>
+__global__ void __launch_bounds__(256) row_quant_wide_kernel(const TIn* __restrict__ x, int m, int c, const RowQuantDev rq) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  const TIn* row = x + static_cast<size_t>(warp) * c;
+  for (int o = 0; o < rq.n_out; ++o) {
+    const QuantDev q = rq.q[o];
+    for (int cv = lane; cv < (c >> 3); cv += 32) {
+      float t[8];
+      load8(row + (cv << 3), t);
+      if (rq.codes[o] == nullptr) quant8_lean(q, t, cv << 3, warp);
+      else quant8(q, t, cv << 3, warp, rq.codes[o] + static_cast<size_t>(warp) * c + (cv << 3));
+      store8(rq.out[o], static_cast<size_t>(warp) * c + (cv << 3), t, q.emit_int, q.emit_int == 2 ? quant_zp(q, warp) : 0.0f);
     }
   }
 }
@@ -612,7 +661,8 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_tile_kernel(const TIn* __res
         const float4 a0 = tile4[(r * 2 + 0) * cvec + cv], a1 = tile4[(r * 2 + 1) * cvec + cv];
         float t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         quant8_lean(q, t, k0, row0 + r);
-        *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * c) = pack8(t);
+        store8(rq.out[o], static_cast<size_t>(row0 + r) * c + k0, t, q.emit_int,
+               q.emit_int == 2 ? quant_zp(q, row0 + r) : 0.0f);
       }
     }
   }
@@ -634,7 +684,7 @@ __global__ void __launch_bounds__(256) geglu_quant_kernel(const TIn* __restrict_
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = a[i] * gelu_erf_f(g[i]);
     quant8_lean(q, a, k0, row);
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * f + k0) = pack8(a);
+    store8(out, static_cast<size_t>(row) * f + k0, a, q.emit_int, q.emit_int == 2 ? quant_zp(q, row) : 0.0f);
   }
 }
 
@@ -769,11 +819,12 @@ static int grid_for(int64_t work, int block, int max_blocks) {
   return static_cast<int>(g < max_blocks ? g : max_blocks);
 }
 static bool quant_ok(const dgq_quant_t& q) {
-  if (q.mode == DGQ_Q_NONE) return true;
+  if (q.mode == DGQ_Q_NONE) return q.emit_int != 2;   // u8 codes need a quantizer
   if (q.mode < 0 || q.mode > DGQ_Q_ROWWISE) return false;
   if (q.delta == nullptr || q.zp == nullptr) return false;
   if (q.mode == DGQ_Q_ROWWISE && q.period <= 0) return false;
   if (q.emit_int && q.mode == DGQ_Q_KWISE) return false;
+  if (q.emit_int < 0 || q.emit_int > 2) return false;
   return true;
 }
 
@@ -850,7 +901,7 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
                             const float* beta, float eps, int n_out, const dgq_quant_t* q, void* const* out,
                             uint8_t* const* codes, void* stream) {
   using namespace dgq;
-  DGQ_CHECK_ARG(x != nullptr && m > 0 && c > 0 && c % 8 == 0 && c <= 12 * 256);
+  DGQ_CHECK_ARG(x != nullptr && m > 0 && c > 0 && c % 8 == 0 && (c <= 12 * 256 || !norm));
   DGQ_CHECK_ARG(n_out >= 1 && n_out <= 3 && q != nullptr && out != nullptr);
   RowQuantDev rq;
   rq.n_out = n_out;
@@ -892,6 +943,11 @@ static int launch_row_quant(const void* x, int src_is_f32, bool norm, int m, int
     DGQ_RETURN_LAST_ERROR();
   }
   const int grid = (m + 7) / 8;  // 8 warps (rows) per CTA
+  if (c > 12 * 256) {
+    if (src_is_f32) row_quant_wide_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), m, c, rq);
+    else row_quant_wide_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), m, c, rq);
+    DGQ_RETURN_LAST_ERROR();
+  }
   const bool narrow = c <= 5 * 256;
   if (norm) {
     DGQ_CHECK_ARG(gamma != nullptr && beta != nullptr);

@@ -158,6 +158,29 @@ __global__ void unpack_weight_kernel(const uint8_t* __restrict__ codes, int bits
   }
 }
 
+// weight codes -> s8 operand of the kind::i8 GEMM + per-row column-sum / offset tables (one warp per output channel)
+__global__ void weight_to_i8_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ zp, int n, int n_pad,
+                                    int k_out, float qmax, int8_t* __restrict__ operand, int32_t* __restrict__ colsum,
+                                    int32_t* __restrict__ b_off) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  const bool real = row < n;
+  const int wz = real ? static_cast<int>(zp[row]) : 0;
+  const int off = qmax <= 127.0f ? wz : 128;
+  int sum = 0;
+  for (int k = lane; k < k_out; k += 32) {
+    const int v = real ? static_cast<int>(codes[static_cast<size_t>(row) * k_out + k]) - off : 0;
+    operand[static_cast<size_t>(row) * k_out + k] = static_cast<int8_t>(v);
+    sum += v;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) {
+    colsum[row] = sum;
+    if (b_off != nullptr) b_off[row] = real ? off - wz : 0;
+  }
+}
+
 static int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g < 1) g = 1;
@@ -226,5 +249,15 @@ extern "C" int dgq_unpack_weight(const uint8_t* codes, int bits, const float* zp
   const int64_t total = static_cast<int64_t>(n_pad) * taps * ci_pad;
   unpack_weight_kernel<<<grid_for(total, 256, kNumSMs * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       codes, bits, zp, n, ci, taps, ci_pad, n_pad, static_cast<__half*>(operand));
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_weight_to_i8(const uint8_t* codes, const float* zp, int n, int n_pad, int k_out, float qmax,
+                                int8_t* operand, int32_t* colsum, int32_t* b_off, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(codes != nullptr && zp != nullptr && operand != nullptr && colsum != nullptr);
+  DGQ_CHECK_ARG(n > 0 && n_pad >= n && k_out > 0 && qmax >= 1.0f && qmax <= 255.0f);
+  weight_to_i8_kernel<<<(n_pad + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, zp, n, n_pad, k_out, qmax,
+                                                                                   operand, colsum, b_off);
   DGQ_RETURN_LAST_ERROR();
 }

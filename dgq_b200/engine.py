@@ -71,19 +71,35 @@ def act_to_tokens(a: Act, dtype=torch.float32) -> torch.Tensor:
 # QuantLayer
 # ------------------------------------------------------------------------------------------
 EXACT_INT = True  # integer A operand + per-row delta in the epilogue wherever the scales allow it
+# kind::i8 qGEMM (u8 activation codes x s8 weight codes, exact s32 accumulation, 2x the MMA rate) for every layer
+# whose activation scale is constant along K: scalar / row-wise quantizers.  K-wise (DGQ group) scales stay on
+# kind::f16 with the scale folded into the operand.  DGQ_I8=0 pins the f16 path (A/B runs).
+USE_I8 = os.environ.get("DGQ_I8", "1") != "0"
 
 
 def _exact(q: ops.QParam) -> bool:
     return EXACT_INT and q.exact
 
 
+def _emit(ql, q: ops.QParam) -> int:
+    """operand form the producer of QuantLayer `ql` writes under quantizer q: 2 = u8 codes (kind::i8 GEMM),
+    1 = integer (code - zp) in fp16 (exact kind::f16 GEMM), 0 = de-quantised fp16."""
+    if not _exact(q):
+        return 0
+    return 2 if (USE_I8 and ql is not None and ql.i8_ok(q)) else 1
+
+
 def _gemm(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, temb=None, rows_per_batch=0, resid=None,
           want_f32=None, **fused):
-    """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q`."""
-    operand, scale, bias, n_pad = ql.packed(geglu=fused.get("epi") == ops.EPI_GEGLU)
+    """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q` (u8 codes: kind::i8)."""
+    i8 = a_op.dtype == torch.uint8
+    pack = ql.packed(geglu=fused.get("epi") == ops.EPI_GEGLU, i8=i8)
+    operand, scale, bias, n_pad = pack[:4]
     if want_f32 is None:
         want_f32 = ops.ACT_DTYPE == torch.float32
-    ex = _exact(q)
+    ex = _exact(q) or i8
+    if i8:
+        fused = dict(fused, colsum=pack[4], b_off=pack[5], row_zp=q.zp)
     return ops.gemm(a_op, operand, n_pad, scale=scale, bias=bias, temb=temb, rows_per_batch=rows_per_batch,
                     resid=resid, want_f32=want_f32, k=operand.shape[1],
                     row_scale=q.delta if ex else None, row_period=q.period if ex else 1, **fused)
@@ -101,7 +117,7 @@ def conv(ql, x: Act, *, x2: Optional[Act] = None, upsample: bool = False, gn=Non
     q = ql.act_qparam(dev)
     a_op = ops.act_producer(x.t, src1=None if x2 is None else x2.t, batch=x.b, h=h, w=w, upsample=upsample,
                             ksize=k, stride=s, gn=gn, act=act, q=q, pad_quantized=ql.pad_quantized,
-                            emit_int=_exact(q))
+                            emit_int=_emit(ql, q))
     out = _gemm(ql, a_op, q, temb=temb, rows_per_batch=ho * wo, resid=resid)
     return Act(out, x.b, ho, wo)
 
@@ -114,7 +130,7 @@ def linear(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, resid: Optional[t
 def quant_rows(x: torch.Tensor, ql) -> Tuple[torch.Tensor, ops.QParam]:
     """quantize rows of x for QuantLayer ql -> (operand, q)"""
     q = ql.act_qparam(x.device)
-    return ops.row_quant(x, [q], emit_int=EXACT_INT)[0], q
+    return ops.row_quant(x, [q], emit_int=_emit(ql, q))[0], q
 
 
 def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
@@ -135,7 +151,7 @@ def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
         if q.mode == ops.Q_KWISE and c % 8:
             raise NotImplementedError("K-wise scales need a channel count that is a multiple of 8")
         a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=k, stride=s, q=q, pad_quantized=ql.pad_quantized,
-                                emit_int=_exact(q))
+                                emit_int=_emit(ql, q))
         pad = k // 2
         ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
         y = _gemm(ql, a_op, q, want_f32=True)
@@ -147,7 +163,7 @@ def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
     x2 = x2.contiguous()
     if q.mode == ops.Q_ROWWISE and (x.dim() != 3 or q.period != shp[-2]):
         raise ValueError(f"row-wise scales for {q.period} tokens do not fit an input of shape {tuple(shp)}")
-    a_op = ops.row_quant(x2, [q], emit_int=EXACT_INT)[0]
+    a_op = ops.row_quant(x2, [q], emit_int=_emit(ql, q))[0]
     y = _gemm(ql, a_op, q, want_f32=True)
     return y[:, :n].reshape(*shp[:-1], n).to(x.dtype)
 
@@ -365,7 +381,7 @@ def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torc
             _qkv_gemm(attn, 2, xv, qs[2], aq[2], b, s, dv, sp)
     qo = attn.to_out[0].act_qparam(dev)
     margs = _map_args(attn, dev, sp) if use_aq else dict(map_mode=ops.MAP_NONE)
-    o, _ = ops.attention(dq, dk, dv, d, out_q=qo, out_emit_int=_exact(qo), **margs)
+    o, _ = ops.attention(dq, dk, dv, d, out_q=qo, out_emit_int=_emit(attn.to_out[0], qo), **margs)
     return linear(attn.to_out[0], o, qo, resid=resid)
 
 
@@ -406,7 +422,7 @@ def cross_kv_prefetch(unet, ctx: torch.Tensor) -> dict:
             sp = bool(getattr(a2, "start_peak", False)) and use_aq
             qs = [None, a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
             aq = [None] + [(_attn_qparam(getattr(a2, n), a2, dev) if use_aq else ops.NOQ) for n in ("aqtizer_k", "aqtizer_v")]
-            xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
+            xkv = ops.row_quant(cx, qs[1:], emit_int=[_emit(a2.to_k, qs[1]), _emit(a2.to_v, qs[2])])
             _qkv_gemm(a2, 1, xkv[0], qs[1], aq[1], cb, s, dk, sp)
             _qkv_gemm(a2, 2, xkv[1], qs[2], aq[2], cb, s, dv, sp)
             ev = torch.cuda.Event()
@@ -432,31 +448,34 @@ def transformer_block(blk, h: Act, ctx: Optional[torch.Tensor], kv_cache: Option
     b, t = h.b, h.rows
     a1, a2, ff = blk.attn1, blk.attn2, blk.ff
     qs = [a1.to_q.act_qparam(dev), a1.to_k.act_qparam(dev), a1.to_v.act_qparam(dev)]
-    xs = ops.ln_quant(h.t, _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps, qs, emit_int=EXACT_INT)
+    xs = ops.ln_quant(h.t, _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps, qs,
+                      emit_int=[_emit(l, q) for l, q in zip((a1.to_q, a1.to_k, a1.to_v), qs)])
     x = attention(a1, xs[0], xs[1], xs[2], qs, b, t, t, resid=h.t)
     if ctx is not None:
         cx, cb, s = _ctx_operand(ctx)
         qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
         xq = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs[:1],
-                          emit_int=EXACT_INT)[0]
+                          emit_int=[_emit(a2.to_q, qs[0])])[0]
         kv = kv_cache.get(id(a2)) if kv_cache else None
         if kv is not None:
             x = attention(a2, xq, None, None, qs, b, t, s, resid=x, kv=kv)
         else:
-            xkv = ops.row_quant(cx, qs[1:], emit_int=EXACT_INT)
+            xkv = ops.row_quant(cx, qs[1:], emit_int=[_emit(a2.to_k, qs[1]), _emit(a2.to_v, qs[2])])
             x = attention(a2, xq, xkv[0], xkv[1], qs, b, t, s, resid=x)
     else:
         qs = [a2.to_q.act_qparam(dev), a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
-        xs = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs, emit_int=EXACT_INT)
+        xs = ops.ln_quant(x, _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps, qs,
+                          emit_int=[_emit(l, q) for l, q in zip((a2.to_q, a2.to_k, a2.to_v), qs)])
         x = attention(a2, xs[0], xs[1], xs[2], qs, b, t, t, resid=x)
     proj, out = ff.net[0].proj, ff.net[2]
     qp = proj.act_qparam(dev)
-    x3 = ops.ln_quant(x, _f32(blk.norm3.weight), _f32(blk.norm3.bias), blk.norm3.eps, [qp], emit_int=EXACT_INT)[0]
+    x3 = ops.ln_quant(x, _f32(blk.norm3.weight), _f32(blk.norm3.bias), blk.norm3.eps, [qp],
+                      emit_int=[_emit(proj, qp)])[0]
     qo = out.act_qparam(dev)
     if FUSE_EPILOGUES and proj.out_features % 64 == 0:
-        g = _gemm(proj, x3, qp, epi=ops.EPI_GEGLU, q2=qo, q2_emit_int=EXACT_INT)
+        g = _gemm(proj, x3, qp, epi=ops.EPI_GEGLU, q2=qo, q2_emit_int=_emit(out, qo))
     else:
-        g = ops.geglu_quant(linear(proj, x3, qp), qo, emit_int=EXACT_INT)
+        g = ops.geglu_quant(linear(proj, x3, qp), qo, emit_int=_emit(out, qo))
     x = linear(out, g, qo, resid=x)
     return Act(x, h.b, h.h, h.w)
 
@@ -470,7 +489,7 @@ def transformer2d(mod, x: Act, ctx: Optional[torch.Tensor], kv_cache: Optional[d
     else:
         qi = mod.proj_in.act_qparam(dev)
         a_op = ops.act_producer(x.t, batch=x.b, h=x.h, w=x.w, ksize=1, gn=_gn(mod.norm, x), q=qi,
-                                emit_int=_exact(qi))
+                                emit_int=_emit(mod.proj_in, qi))
         h = Act(linear(mod.proj_in, a_op, qi), x.b, x.h, x.w)
     for blk in mod.transformer_blocks:
         h = transformer_block(blk, h, ctx, kv_cache)

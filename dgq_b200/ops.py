@@ -59,8 +59,9 @@ class QParam:
     qmax: float = 255.0
     int_ok: bool = False   # |code - zp| <= 2048 for every entry: the integer operand is exact in fp16
     inv: Optional[torch.Tensor] = None   # 1/delta (IEEE), for the quantizer's multiply fast path
+    zp_in_range: bool = False   # 0 <= zp <= qmax everywhere: an exact 0 (conv zero padding) is the u8 code zp
 
-    def struct(self, emit_int: bool = False) -> L.QuantT:
+    def struct(self, emit_int: int = 0) -> L.QuantT:
         if self.inv is None and self.delta is not None:
             self.inv = torch.reciprocal(self.delta)
         return L.QuantT(_p(self.delta), _p(self.zp), _p(self.inv), self.mode, self.period, self.qmax, int(emit_int))
@@ -83,9 +84,10 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     re-orders a K-wise table into the GEMM's K order (conv: tap-major)."""
     d, z = _f32(delta, device), _f32(zp, device)
     int_ok = bool((z.abs().max() + qmax <= 2048).item())
+    in_range = bool(((z.min() >= 0) & (z.max() <= qmax)).item())
     if d.dim() == 0 or d.numel() == 1 and d.dim() <= 1:
         d1 = d.reshape(1)
-        return QParam(Q_SCALAR, d1, z.reshape(1).expand(1).contiguous(), 1, qmax, int_ok, torch.reciprocal(d1))
+        return QParam(Q_SCALAR, d1, z.reshape(1).expand(1).contiguous(), 1, qmax, int_ok, torch.reciprocal(d1), in_range)
     if d.dim() == 3 and d.shape[0] == 1 and d.shape[1] == 1:      # (1,1,X): last axis
         mode = Q_ROWWISE if conv else Q_KWISE
     elif d.dim() == 3 and d.shape[0] == 1 and d.shape[2] == 1:    # (1,X,1): middle axis
@@ -96,7 +98,7 @@ def qparam_from_ckpt(delta: torch.Tensor, zp: torch.Tensor, qmax: float, device,
     if kperm is not None and mode == Q_KWISE:
         d, z = d[kperm], z[kperm]
     d = d.contiguous()
-    return QParam(mode, d, z.contiguous(), d.numel(), qmax, int_ok, torch.reciprocal(d))
+    return QParam(mode, d, z.contiguous(), d.numel(), qmax, int_ok, torch.reciprocal(d), in_range)
 
 
 # ------------------------------------------------------------------------------------------
@@ -171,9 +173,9 @@ def unpack_weight(codes: torch.Tensor, bits: int, zp: torch.Tensor, n: int, ci: 
 def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Optional[torch.Tensor] = None,
                  upsample: bool = False, ksize: int = 1, stride: int = 1, gn=None, act: int = 0,
                  q: QParam = NOQ, pad_quantized: bool = False, ldo: Optional[int] = None,
-                 want_codes: bool = False, emit_int: bool = False):
-    """src NHWC ([batch, hs, ws, c], fp16 or fp32) -> fp16 A operand [M, ldo] (+ codes).
-    gn = (mean, rstd, gamma, beta) or None."""
+                 want_codes: bool = False, emit_int: int = 0):
+    """src NHWC ([batch, hs, ws, c], fp16 or fp32) -> fp16 A operand [M, ldo] (+ codes); emit_int = 2: the u8
+    code operand of the kind::i8 GEMM.  gn = (mean, rstd, gamma, beta) or None."""
     c0 = src0.shape[-1]
     c1 = src1.shape[-1] if src1 is not None else 0
     pad = 1 if ksize == 3 else 0
@@ -182,7 +184,8 @@ def act_producer(src0: torch.Tensor, *, batch: int, h: int, w: int, src1: Option
     K = ksize * ksize * (c0 + c1)
     ldo = ldo or K
     M = batch * ho * wo
-    out = torch.empty(M, ldo, dtype=torch.float16, device=src0.device)
+    emit_int = int(emit_int)
+    out = torch.empty(M, ldo, dtype=torch.uint8 if emit_int == 2 else torch.float16, device=src0.device)
     codes = torch.empty(M, K, dtype=torch.uint8, device=src0.device) if want_codes else None
     a = L.ProducerT(_p(src0), _p(src1), c0, c1, int(src0.dtype == torch.float32), batch, h, w, int(upsample),
                     ksize, stride, pad,
@@ -206,16 +209,25 @@ def gn_stats(src0: torch.Tensor, src1: Optional[torch.Tensor], batch: int, hw: i
     return mean, rstd
 
 
-def _row_outputs(x, qs, emit_int=False):
+def _emit_modes(qs, emit_int):
+    """per-quantizer operand form: 0 de-quantised fp16, 1 integer (code - zp) fp16, 2 u8 codes.  A scalar applies to
+    every quantizer that allows it (K-wise scales must be folded: always 0)."""
+    if isinstance(emit_int, (list, tuple)):
+        return [int(e) if q.exact else 0 for e, q in zip(emit_int, qs)]
+    return [int(emit_int) if q.exact else 0 for q in qs]
+
+
+def _row_outputs(x, qs, emit_int=0):
     m, c = x.shape
-    outs = [torch.empty(m, c, dtype=torch.float16, device=x.device) for _ in qs]
-    qarr = (L.QuantT * len(qs))(*[q.struct(emit_int and q.exact) for q in qs])
+    modes = _emit_modes(qs, emit_int)
+    outs = [torch.empty(m, c, dtype=torch.uint8 if e == 2 else torch.float16, device=x.device) for e in modes]
+    qarr = (L.QuantT * len(qs))(*[q.struct(e) for q, e in zip(qs, modes)])
     oarr = (C.c_void_p * len(qs))(*[o.data_ptr() for o in outs])
     return outs, qarr, oarr
 
 
 def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, qs: Sequence[QParam],
-             emit_int: bool = False):
+             emit_int=0):
     """x [m, c] -> [fp16 [m, c]] * len(qs); emit_int: integer operands for the quantizers that allow it."""
     outs, qarr, oarr = _row_outputs(x, qs, emit_int)
     L.check(L.lib().dgq_ln_quant(_p(x), _is32(x), x.shape[0], x.shape[1], _p(gamma), _p(beta), eps, len(qs), qarr,
@@ -224,7 +236,7 @@ def ln_quant(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: floa
     return outs
 
 
-def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False, emit_int: bool = False):
+def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False, emit_int=0):
     outs, qarr, oarr = _row_outputs(x, qs, emit_int)
     codes = [torch.empty(x.shape, dtype=torch.uint8, device=x.device) for _ in qs] if want_codes else None
     carr = (C.c_void_p * len(qs))(*[c.data_ptr() for c in codes]) if want_codes else None
@@ -234,10 +246,11 @@ def row_quant(x: torch.Tensor, qs: Sequence[QParam], want_codes: bool = False, e
     return (outs, codes) if want_codes else outs
 
 
-def geglu_quant(x: torch.Tensor, q: QParam, emit_int: bool = False) -> torch.Tensor:
+def geglu_quant(x: torch.Tensor, q: QParam, emit_int: int = 0) -> torch.Tensor:
     m, f2 = x.shape
-    out = torch.empty(m, f2 // 2, dtype=torch.float16, device=x.device)
-    L.check(L.lib().dgq_geglu_quant(_p(x), _is32(x), m, f2 // 2, q.struct(emit_int and q.exact), _p(out), _stream()),
+    e = _emit_modes([q], emit_int)[0]
+    out = torch.empty(m, f2 // 2, dtype=torch.uint8 if e == 2 else torch.float16, device=x.device)
+    L.check(L.lib().dgq_geglu_quant(_p(x), _is32(x), m, f2 // 2, q.struct(e), _p(out), _stream()),
             "dgq_geglu_quant")
     _count()
     return out
@@ -246,7 +259,9 @@ def geglu_quant(x: torch.Tensor, q: QParam, emit_int: bool = False) -> torch.Ten
 def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, temb=None, rows_per_batch: int = 0,
          resid=None, out: Optional[torch.Tensor] = None, want_f32: bool = False, k: Optional[int] = None,
          row_scale: Optional[torch.Tensor] = None, row_period: int = 1, epi: int = L.EPI_PLAIN,
-         q2: QParam = NOQ, q2_emit_int: bool = False, qkv: Optional[tuple] = None):
+         q2: QParam = NOQ, q2_emit_int: int = 0, qkv: Optional[tuple] = None,
+         colsum: Optional[torch.Tensor] = None, b_off: Optional[torch.Tensor] = None,
+         row_zp: Optional[torch.Tensor] = None):
     """a fp16 [m, lda], b fp16 [n_pad, ldb] -> [m, n] (n multiple of 8), fp32 if want_f32 (or `out`
     is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32).
     epi = EPI_GEGLU: b rows interleaved (pack_weight geglu=True); returns the fp16 operand [m, n/2] of
@@ -254,8 +269,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
     (heads, d, dp, tokens, tp, transpose, skip_first)."""
     m = a.shape[0]
     k = k or min(a.shape[1], b.shape[1])
+    i8 = a.dtype == torch.uint8           # u8 activation codes x s8 weight codes: dgq_gemm_i8
+    if i8 and (b.dtype != torch.int8 or colsum is None or row_zp is None or row_scale is None):
+        raise TypeError("gemm: a u8 A operand needs the s8 weight operand with its colsum / row_zp / row_scale")
+    e2 = _emit_modes([q2], q2_emit_int)[0] if q2.mode != Q_NONE else 0
     if epi == L.EPI_GEGLU:
-        out = torch.empty(m, n // 2, dtype=torch.float16, device=a.device)
+        out = torch.empty(m, n // 2, dtype=torch.uint8 if e2 == 2 else torch.float16, device=a.device)
     elif epi == L.EPI_QKV:
         assert out is not None and out.dtype == torch.float16 and qkv is not None
     elif out is None:
@@ -273,10 +292,29 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
                 _p(temb), rows_per_batch,
                 temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
                 None if o32 else _p(out), ldc, _p(out) if o32 else None, ep32,
-                epi, q2.struct(q2_emit_int and q2.exact), heads, d, dp, tokens, tp, int(transpose), int(skip_first))
-    L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
+                epi, q2.struct(e2), heads, d, dp, tokens, tp, int(transpose), int(skip_first),
+                _p(colsum), _p(b_off), _p(row_zp))
+    if i8:
+        L.check(L.lib().dgq_gemm_i8(C.byref(g), _stream()), "dgq_gemm_i8")
+    else:
+        L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
     _count()
     return out
+
+
+def weight_to_i8(codes: torch.Tensor, zp: torch.Tensor, n: int, qmax: float):
+    """u8 weight codes [n_pad, k] (dgq_pack_weight) -> (s8 operand, colsum int32 [n_pad], b_off int32 [n_pad] | None)."""
+    n_pad, k = codes.shape
+    operand = torch.empty(n_pad, k, dtype=torch.int8, device=codes.device)
+    colsum = torch.empty(n_pad, dtype=torch.int32, device=codes.device)
+    b_off = torch.empty(n_pad, dtype=torch.int32, device=codes.device) if qmax > 127 else None
+    z = _f32(zp, codes.device).reshape(-1)
+    if z.numel() == 1 and n > 1:
+        z = z.expand(n).contiguous()
+    L.check(L.lib().dgq_weight_to_i8(_p(codes), _p(z), n, n_pad, k, qmax, _p(operand), _p(colsum), _p(b_off), _stream()),
+            "dgq_weight_to_i8")
+    _count()
+    return operand, colsum, b_off
 
 
 def qkv_dest(b: int, t: int, heads: int, d: int, dp: int, transpose: bool, device) -> torch.Tensor:
@@ -301,13 +339,14 @@ def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, tr
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map_mode: int, real_time: bool = False,
               start_peak: bool = False, delta: Optional[torch.Tensor] = None, qmax: float = 255.0,
               out: Optional[torch.Tensor] = None, want_codes: bool = False, out_dtype=torch.float16,
-              out_q: Optional[QParam] = None, out_emit_int: bool = False):
+              out_q: Optional[QParam] = None, out_emit_int: int = 0):
     """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta[, codes])."""
     b, heads, t, dp = q.shape
     s, sp = k.shape[2], vt.shape[3]
     dev = q.device
-    if out_q is not None:     # fused quantizer of the consumer: the result IS its fp16 GEMM operand
-        out_dtype = torch.float16
+    oe = _emit_modes([out_q], out_emit_int)[0] if out_q is not None and out_q.mode != Q_NONE else 0
+    if out_q is not None:     # fused quantizer of the consumer: the result IS its GEMM operand (fp16, or u8 codes)
+        out_dtype = torch.uint8 if oe == 2 else torch.float16
     if out is None:
         out = torch.empty(b * t, heads * d, dtype=out_dtype, device=dev)
     row_max = torch.empty(b * heads * t, dtype=torch.float32, device=dev)
@@ -317,7 +356,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map
     codes = torch.zeros(b, heads, t, s, dtype=torch.uint8, device=dev) if want_codes else None
     a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
                 int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0),
-                _is32(out), _p(codes), (out_q or NOQ).struct(out_emit_int and (out_q or NOQ).exact))
+                int(out.dtype == torch.float32), _p(codes), (out_q or NOQ).struct(oe))
     L.check(L.lib().dgq_attention(C.byref(a), _stream()), "dgq_attention")
     _count(2)
     return (out, gmax[:1], codes) if want_codes else (out, gmax[:1])

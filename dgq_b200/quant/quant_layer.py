@@ -270,9 +270,26 @@ class QuantLayer(nn.Module):
         return hit[1]
 
     # -- packed weights (K2: once, not per forward) -----------------------------------------
-    def packed(self, geglu: bool = False):
+    def i8_ok(self, q: "ops.QParam") -> bool:
+        """this layer can run on the kind::i8 qGEMM under activation quantizer q: quantized W4 / W8 weights, an
+        activation scale that is constant along K (scalar / row-wise), byte operands with 16-byte rows, and -- for
+        a conv on the per-tensor path, whose zero padding is an exact 0 (reference :659) -- a zero point that is
+        itself a code (0 <= zp <= qmax), so that padding taps can be written as the code zp."""
+        if not (self.use_wq and q.exact and self.wqtizer.level in (16, 256)) or self._frozen is not None:
+            return False
+        k = self.w[0].numel()
+        if k % 16:
+            return False
+        if self.is_conv and self.ksize > 1 and not self.pad_quantized and not q.zp_in_range:
+            return False
+        return True
+
+    def packed(self, geglu: bool = False, i8: bool = False):
         """(operand fp16 [n_pad, K], scale fp32 [n_pad] | None, bias fp32 [n_pad] | None, n_pad).
-        geglu: rows interleaved for the fused GEGLU epilogue (cached separately)."""
+        geglu: rows interleaved for the fused GEGLU epilogue (cached separately).
+        i8: the s8 operand of dgq_gemm_i8 instead, + (colsum int32 [n_pad], b_off int32 [n_pad] | None)."""
+        if i8:
+            return self._packed_i8(geglu)
         if self._frozen is not None:
             return self._frozen_pack(geglu)
         w = self.w if self.use_wq else self.original_w
@@ -321,6 +338,46 @@ class QuantLayer(nn.Module):
             self._pack = {}
         self._pack[geglu] = (key, (operand, scale, bias, n_pad))
         return self._pack[geglu][1]
+
+    def _packed_i8(self, geglu: bool):
+        """kind::i8 operand: s8 (code - off_n), off_n = zp_n for W4 (exact, nothing left to correct) or 128 for W8,
+        with the per-channel column sums and residual offsets of dgq_gemm_i8's integer epilogue."""
+        w, b, wq = self.w, self.b, self.wqtizer
+        _need_cuda(w, "QuantLayer weights")
+        if wq.delta is None:
+            wq.delta, wq.zero_point = channel_minmax(self.w, wq.level)
+            wq.init = True
+        alpha = getattr(wq, "alpha", None)
+        key = ("i8", id(w), w._version, None if b is None else (id(b), b._version), geglu, id(wq.delta),
+               wq.delta._version, id(wq.zero_point), wq.zero_point._version,
+               None if alpha is None else (id(alpha), alpha._version))
+        hit = self._pack.get(("i8", geglu)) if self._pack else None
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dev, n = w.device, w.shape[0]
+        n_pad = (n + 7) // 8 * 8
+        qmax = float(wq.level - 1)
+        _, codes, _ = ops.pack_weight(w.detach().to(torch.float32), wq.delta, wq.zero_point, alpha, qmax, True,
+                                      n_pad=n_pad, want_codes=True)
+        operand, colsum, b_off = ops.weight_to_i8(codes, wq.zero_point, n, qmax)
+        scale = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        scale[:n] = wq.delta.detach().reshape(-1).to(dev, torch.float32)
+        bias = None
+        if b is not None:
+            bias = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+            bias[:n] = b.detach().to(dev, torch.float32)
+        if geglu:
+            if n % 64 or n_pad != n:
+                raise ValueError("GEGLU interleave needs 2f to be a multiple of 64")
+            i = torch.arange(n, device=dev)
+            perm = (i // 64) * 32 + i % 32 + ((i % 64) >= 32) * (n // 2)
+            operand, scale, colsum = operand[perm].contiguous(), scale[perm].contiguous(), colsum[perm].contiguous()
+            bias = None if bias is None else bias[perm].contiguous()
+            b_off = None if b_off is None else b_off[perm].contiguous()
+        if not self._pack:
+            self._pack = {}
+        self._pack[("i8", geglu)] = (key, (operand, scale, bias, n_pad, colsum, b_off))
+        return self._pack[("i8", geglu)][1]
 
     def _frozen_pack(self, geglu: bool):
         """Operands of a compiled checkpoint (no fp32 master weights on the device)."""

@@ -94,11 +94,11 @@ class Attention(nn.Module):
         qs = [self.to_q.act_qparam(dev), self.to_k.act_qparam(dev), self.to_v.act_qparam(dev)]
         if encoder_hidden_states is not None:
             cx, _, s = engine._ctx_operand(encoder_hidden_states)
-            xq = ops.row_quant(x, qs[:1], emit_int=engine.EXACT_INT)[0]
-            xk, xv = ops.row_quant(cx, qs[1:], emit_int=engine.EXACT_INT)
+            xq = ops.row_quant(x, qs[:1], emit_int=[engine._emit(self.to_q, qs[0])])[0]
+            xk, xv = ops.row_quant(cx, qs[1:], emit_int=[engine._emit(self.to_k, qs[1]), engine._emit(self.to_v, qs[2])])
         else:
             s = t
-            xq, xk, xv = ops.row_quant(x, qs, emit_int=engine.EXACT_INT)
+            xq, xk, xv = ops.row_quant(x, qs, emit_int=[engine._emit(l, q) for l, q in zip((self.to_q, self.to_k, self.to_v), qs)])
         out = engine.attention(self, xq, xk, xv, qs, b, t, s, resid=None)
         return out.view(b, t, -1).to(hidden_states.dtype)
 

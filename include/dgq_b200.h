@@ -46,9 +46,11 @@ typedef struct {
   int mode;     /* DGQ_Q_*            */
   int period;   /* DGQ_Q_ROWWISE only */
   float qmax;   /* 2^bits - 1         */
-  int emit_int; /* producers only: write the integer (code - zp), exact in fp16, instead of
+  int emit_int; /* producers only: 1 = write the integer (code - zp), exact in fp16, instead of
                    delta * (code - zp); the consumer GEMM applies delta per row (row_scale).
-                   Valid for SCALAR / ROWWISE, |code - zp| <= 2048.                          */
+                   Valid for SCALAR / ROWWISE, |code - zp| <= 2048.
+                   2 = write the u8 CODE itself, one byte per element (operand of dgq_gemm_i8;
+                   the output row stride is then in bytes).  SCALAR / ROWWISE only.           */
 } dgq_quant_t;
 
 int dgq_version(void);
@@ -168,11 +170,34 @@ typedef struct {
   int epi;             /* DGQ_EPI_* */
   dgq_quant_t q2;
   int heads, d, dp, tokens, tp, transpose, skip_first;
+  /* ---- dgq_gemm_i8 only (ignored by dgq_gemm_f16): integer zero-point corrections, see below */
+  const int32_t* colsum; /* [n] sum_k B[n, k] (dgq_weight_to_i8)                                     */
+  const int32_t* b_off;  /* [n] e_n = (offset subtracted from the weight codes) - (weight zero point),
+                            or NULL when the zero point itself was subtracted (W4: codes - zp fit s8)  */
+  const float* row_zp;   /* activation zero point, indexed like row_scale: row_zp[m % row_period]     */
 } dgq_gemm_t;
 #define DGQ_EPI_PLAIN 0
 #define DGQ_EPI_GEGLU 1
 #define DGQ_EPI_QKV 2
 int dgq_gemm_f16(const dgq_gemm_t* host_args, void* stream);
+
+/* ---- the same GEMM on tcgen05 kind::i8 (2x the MMA rate; profiles/r2_probes.txt, r2_gemm_i8_vs_f16.txt) for
+ *      layers whose activation scale is constant along K (scalar or row-wise: quant/quant_layer.py:295-299 with a
+ *      () or per-row delta -- every layer of the group_num = 1 configs).
+ * A: u8 activation CODES [m, lda] (producers with dgq_quant_t.emit_int = 2); B: s8 [n_pad, ldb] from
+ * dgq_weight_to_i8; k, lda, ldb multiples of 16.  The accumulation is exact (s32) and the zero points are removed
+ * in integer arithmetic in the epilogue:
+ *   sum_k (a_mk - za_m)(w_nk - wz_n) = acc_mn - za_m * colsum_n + e_n * (rowsum_m - k * za_m)
+ * (rowsum_m = sum_k a_mk is computed inside the kernel, only when b_off != NULL), then
+ *   C = that * row_scale[m] * scale[n] + bias[n] (+ temb) (+ resid), epilogues as dgq_gemm_f16.
+ * row_scale (activation delta) and row_zp are required.                                                     */
+int dgq_gemm_i8(const dgq_gemm_t* host_args, void* stream);
+
+/* weight codes (u8 [n_pad, k_out], GEMM K order, from dgq_pack_weight) -> s8 operand of dgq_gemm_i8 + tables:
+ *   operand[n, k] = code - off_n, off_n = zp[n] when qmax <= 127 (W4: exact, b_off[n] = 0) else 128
+ *   (b_off[n] = 128 - zp[n]); colsum[n] = sum_k operand[n, k]; rows >= n are zero.                           */
+int dgq_weight_to_i8(const uint8_t* codes, const float* zp, int n, int n_pad, int k_out, float qmax,
+                     int8_t* operand, int32_t* colsum, int32_t* b_off, void* stream);
 
 /* ---- attention with quantised operands and quantised softmax map
  *      (Attention.Attention_forward, diffusers_rewrite/sd.py:151-207; T2ILogQuantizer) ---------

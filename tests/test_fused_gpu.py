@@ -30,7 +30,8 @@ def _interleave(n):
 
 
 @pytest.mark.parametrize("m,f,k", [(256, 64, 128), (300, 320, 192), (4096, 1280, 320), (16384, 5120, 640)])
-@pytest.mark.parametrize("mode,emit", [("kwise", False), ("scalar", True), ("rowwise", True), ("none", False)])
+@pytest.mark.parametrize("mode,emit", [("kwise", False), ("scalar", True), ("rowwise", True), ("none", False),
+                                       ("scalar", 2), ("rowwise", 2)])     # 2: u8 codes for a kind::i8 consumer
 def test_geglu_epilogue(m, f, k, mode, emit):
     from dgq_b200 import ops
     g = torch.Generator().manual_seed(m + f + k)
@@ -72,8 +73,8 @@ def test_qkv_epilogue(b_, t, heads, d, mode, transpose, skip):
     assert torch.equal(dst, ref), (dst.float() - ref.float()).abs().max().item()
 
 
-@pytest.mark.parametrize("mode,emit", [("kwise", False), ("scalar", True), ("rowwise", True)])
-@pytest.mark.parametrize("t,s,heads,d", [(256, 256, 8, 40), (1024, 77, 10, 64)])
+@pytest.mark.parametrize("mode,emit", [("kwise", False), ("scalar", True), ("rowwise", True), ("scalar", 2), ("rowwise", 2)])
+@pytest.mark.parametrize("t,s,heads,d", [(256, 256, 8, 40), (1024, 77, 10, 64), (4096, 4096, 2, 64)])
 def test_attention_out_quant(t, s, heads, d, mode, emit):
     from dgq_b200 import ops
     g = torch.Generator().manual_seed(t + s + d)
