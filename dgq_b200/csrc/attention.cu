@@ -69,6 +69,11 @@ struct AttnDev {
   int out_is_f32;
   uint8_t* codes;
   // quantizer of the consuming QuantLayer (to_out[0]) applied to O in the epilogue
+  // score scales: Q is the bare integer (code - zp) and K carries every K-side / per-channel scale (hi | lo split, see
+  // dgq_gemm_t.k_split); q_scale[row % period] = the Q quantizer's scalar / per-token delta, applied through alpha
+  const float* q_scale;
+  int q_period;
+  int k_split;
   const float* oq_delta;
   const float* oq_zp;
   const float* oq_inv;
@@ -174,12 +179,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   // epilogue / softmax accesses compile to LDS / STS instead of generic LD / ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int dchunks = p.dp >> 6;
-  const uint32_t q_bytes = dchunks * kChunkBytes;          // one Q tile / one K stage
+  const uint32_t q_bytes = dchunks * kChunkBytes;          // one Q tile
+  const uint32_t k_bytes = p.k_split ? 2 * q_bytes : q_bytes;   // one K stage: hi chunks, then lo chunks
+  const int kchunks = p.k_split ? 2 * dchunks : dchunks;
   const uint32_t v_stage = 2 * p.dp * 128;                 // two [dp x 64] sub-tiles
   const uint32_t nqb = p.nq_buf, nkb = p.nk_buf, nvb = p.nv_buf, nob = p.no_buf, nh = p.nh;
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + nqb * q_bytes;
-  uint8_t* s_v = s_k + nkb * q_bytes;
+  uint8_t* s_v = s_k + nkb * k_bytes;
   uint8_t* s_p = s_v + (PASS == 2 ? nvb * v_stage : 0);
   uint8_t* s_end = s_p + (PASS == 2 ? 2 * 2 * kChunkBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_end);
@@ -232,9 +239,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < p.nkv; ++j, ++g) {
           const uint32_t slot = g % nkb;
           mbar_wait(&bars[B_KEMPTY + slot], ((g / nkb) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
-          for (int c = 0; c < dchunks; ++c)
-            tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], c * 64, j * kTileK, bh);
+          mbar_arrive_expect_tx(&bars[B_KFULL + slot], k_bytes);
+          for (int c = 0; c < kchunks; ++c)
+            tma_load_3d(s_k + slot * k_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], c * 64, j * kTileK, bh);
         }
       }
     }
@@ -301,9 +308,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
             mbar_wait(&bars[B_SEMPTY + sb], ((u >> 1) & 1) ^ 1);
             tc_fence_after();
-            for (int c = 0; c < dchunks; ++c) {
-              const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + c * kChunkBytes));
-              const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * q_bytes + c * kChunkBytes));
+            for (int c = 0; c < kchunks; ++c) {    // Q . K_hi, then Q . K_lo into the same accumulator
+              const int cq = c < dchunks ? c : c - dchunks;
+              const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + cq * kChunkBytes));
+              const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * k_bytes + c * kChunkBytes));
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (c | ks) != 0 ? 1u : 0u);
@@ -335,11 +343,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       int tq[2];
       bool row_ok[2];
       size_t ridx[2];
+      float al[2];                                  // alpha of the row: scale * log2(e) * (delta of its Q quantizer)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         tq[h] = (qg * static_cast<int>(nh) + h) * kTileQ + row;   // query index
         row_ok[h] = h < static_cast<int>(nh) && tq[h] < p.t;
         ridx[h] = static_cast<size_t>(bh) * p.t + tq[h];
+        al[h] = p.alpha * ((p.q_scale != nullptr && row_ok[h]) ? __ldg(p.q_scale + tq[h] % p.q_period) : 1.0f);
       }
 
       // O accumulator `ob`, columns [c_lo, c_hi) of this thread's row: O * out_scale (+ p0 * v0), the to_out quantizer, store
@@ -464,6 +474,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int tqh = (qg * 2 + grp) * kTileQ + row;
         const bool rok = tqh < p.t;
         const size_t rix = static_cast<size_t>(bh) * p.t + tqh;
+        const float alpha = p.alpha * ((p.q_scale != nullptr && rok) ? __ldg(p.q_scale + tqh % p.q_period) : 1.0f);
         float delta = 1.0f;
         if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
         const float lg_delta = MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f;
@@ -496,10 +507,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
             }
             uint32_t h2[16];
-            map_chunk<MODE, CODES>(r, h2, p.alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len, code_row);
+            map_chunk<MODE, CODES>(r, h2, alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len, code_row);
             if (cc == 0) {
               if (p.start_peak && j == 0 && half == 0) {
-                p0 = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0]), -beta));
+                p0 = ex2_approx(fmaf(alpha, __uint_as_float(r[0]), -beta));
                 h2[0] &= 0xFFFF0000u;             // column 0 leaves the MMA; added back in the epilogue
               }
               mbar_wait(&bars[B_PEMPTY + sb], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
@@ -564,15 +575,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               float cm = x[1];
 #pragma unroll
               for (int i = 2; i < 32; ++i) cm = fmaxf(cm, x[i]);
-              const float cmx = cm * p.alpha;       // excludes element 0 of this chunk
-              cm = fmaxf(cm, x[0]) * p.alpha;
+              const float cmx = cm * al[h];         // excludes element 0 of this chunk
+              cm = fmaxf(cm, x[0]) * al[h];
               Mx[h] = fmaxf(Mx[h], (j == 0 && c == 0) ? cmx : cm);
               const float Mn = fmaxf(M[h], cm);
               if (Mn > -INFINITY) {
                 float acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                  const float e = fmaf(x[i], p.alpha, -Mn);
+                  const float e = fmaf(x[i], al[h], -Mn);
                   acc += (i % kPolyEvery) == kPolyEvery - 1 ? ex2_poly(e) : ex2_approx(e);
                 }
                 l[h] = l[h] * ex2_approx(M[h] - Mn) + acc;
@@ -640,10 +651,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             uint32_t h2[kCh][16];
 #pragma unroll
             for (int cc = 0; cc < kCh; ++cc)
-              map_chunk<MODE, CODES>(r[cc], h2[cc], p.alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len,
+              map_chunk<MODE, CODES>(r[cc], h2[cc], al[h], gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len,
                                      code_row);
             if (p.start_peak && j == 0 && half == 0) {
-              p0[h] = ex2_approx(fmaf(p.alpha, __uint_as_float(r[0][0]), -beta[h]));
+              p0[h] = ex2_approx(fmaf(al[h], __uint_as_float(r[0][0]), -beta[h]));
               h2[0][0] &= 0xFFFF0000u;              // column 0 leaves the MMA; added back in the epilogue
             }
             mbar_wait(&bars[B_PEMPTY + sb], ph ^ 1);   // PV of step u - 2 has consumed this P' buffer
@@ -728,6 +739,8 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   DGQ_CHECK_ARG(a->out_q.mode >= DGQ_Q_NONE && a->out_q.mode <= DGQ_Q_ROWWISE);
   DGQ_CHECK_ARG(a->out_q.mode == DGQ_Q_NONE || (a->out_q.delta != nullptr && a->out_q.zp != nullptr));
   DGQ_CHECK_ARG(!(a->out_q.emit_int && a->out_q.mode == DGQ_Q_KWISE));
+  DGQ_CHECK_ARG(!(a->k_split && a->dp > 128));           // shared memory: dp = 192 has no room for the lo tiles
+  DGQ_CHECK_ARG(a->q_scale == nullptr || a->q_scale_period > 0);
   DGQ_CHECK_ARG(a->out_q.emit_int != 2 || (a->out_q.mode != DGQ_Q_NONE && !a->out_is_f32 && a->ldo % 16 == 0));
 
   AttnDev p;
@@ -738,10 +751,19 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   // so dp = 192 runs nh = 1 with a single O accumulator.  smem (227 KB), in 16 KB units for dp = 64:
   // Q 4 + K 3 + V 2 + P' 4; dp = 128: Q 2 + K 1 + V 1 (32 KB units) + P'; dp = 192: Q 1 + K 1 + V 1 (48 KB) + P'.
   p.q_tiles = (a->t + kTileQ - 1) / kTileQ;
-  p.nh = (a->dp <= 128 && p.q_tiles > 1) ? 2 : 1;
-  p.nq_buf = a->dp <= 64 ? 4 : (a->dp <= 128 ? 2 : 1);
-  p.nk_buf = a->dp <= 64 ? 3 : 1;
-  p.nv_buf = a->dp <= 64 ? 2 : 1;
+  p.k_split = a->k_split ? 1 : 0;
+  p.q_scale = a->q_scale; p.q_period = a->q_scale_period > 0 ? a->q_scale_period : 1;
+  if (!p.k_split) {
+    p.nh = (a->dp <= 128 && p.q_tiles > 1) ? 2 : 1;
+    p.nq_buf = a->dp <= 64 ? 4 : (a->dp <= 128 ? 2 : 1);
+    p.nk_buf = a->dp <= 64 ? 3 : 1;
+    p.nv_buf = a->dp <= 64 ? 2 : 1;
+  } else {     // K stages are twice as large (hi | lo): dp = 64: Q 2 + K 2 x 2 + V 2 + P' 4 (16 KB units) = 192 KB
+    p.nh = (a->dp <= 64 && p.q_tiles > 1) ? 2 : 1;
+    p.nq_buf = a->dp <= 64 ? 2 : 1;
+    p.nk_buf = a->dp <= 64 ? 2 : 1;
+    p.nv_buf = a->dp <= 64 ? 2 : 1;
+  }
   p.no_buf = a->dp <= 128 ? 2 : 1;
   p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
   p.alpha = a->scale * 1.4426950408889634f;
@@ -758,17 +780,18 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   CUtensorMap tq, tk, tv;
   int rc = make_tmap_3d(&tq, a->q, bh, a->t, a->dp, kTileQ);
   if (rc != 0) return rc;
-  rc = make_tmap_3d(&tk, a->k, bh, a->s, a->dp, kTileK);
+  rc = make_tmap_3d(&tk, a->k, bh, a->s, p.k_split ? 2 * a->dp : a->dp, kTileK);   // k_split: [.., s, hi dp | lo dp]
   if (rc != 0) return rc;
   rc = make_tmap_3d(&tv, a->vt, bh, a->dp, a->sp, a->dp);
   if (rc != 0) return rc;
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
+  const uint32_t k_bytes = p.k_split ? 2 * q_bytes : q_bytes;
   const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 4 * 192 * 4 + 3 * 128 * 4 + 64;
   AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring
   if (p1.nq_buf > 2) p1.nq_buf = 2;
-  const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
-  const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
+  const uint32_t smem1 = q_bytes * p1.nq_buf + k_bytes * p1.nk_buf + tail;
+  const uint32_t smem2 = q_bytes * p.nq_buf + k_bytes * p.nk_buf + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
   KernelFn k1 = attention_kernel<1, 0, false, false>;
   KernelFn k2;

@@ -41,7 +41,7 @@ constexpr int kMaxBN = 256;
 // instructions per result, so with 2 warps per scheduler they, not the MMAs, bounded the tile time
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kStgLd = 36;                         // padded row stride (floats) of the fp32 epilogue transpose buffer
-constexpr int kEpiTab = 8;                         // per-column tables staged per tile
+constexpr int kEpiTab = 9;                         // per-column tables staged per tile
 constexpr int kRsRing = 8;                         // kI8: ring of per-tile row-sum vectors (row-sum warps run ahead)
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
 template <int kEpi, bool kI8 = false> struct EpiCfg {
@@ -89,6 +89,12 @@ struct GemmDev {
   EpiQuant q2;
   // EPI_QKV geometry: GEMM row = (batch, token), column = (head, channel)
   int heads, d, dp, tokens, tp, transpose, skip_first;
+  // EPI_QKV, K operand of the attention kernel: every scale of the score is folded into K (kfold[d] = the Q
+  // quantizer's per-channel delta, or nullptr) and K is written as an fp16 hi | lo pair ([b, h, tokens, 2 dp]) so
+  // that Q (integer codes - zp) . K carries ~22 bits: the softmax-map codes then follow the reference's to its own
+  // fp32 rounding level (tests/test_layerwise_gpu.py)
+  const float* kfold;
+  int k_split;
   // kI8
   const int32_t* colsum;   // [n] sum_k B[n, k]
   const int32_t* b_off;    // [n] e_n = b_off_n - wz_n, or nullptr (= 0: the weight zero point is folded into B)
@@ -296,6 +302,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       float* s_qh = s_qz + kMaxBN;      // hi = qmax - zp
       int* s_cs = reinterpret_cast<int*>(s_qh + kMaxBN);   // kI8: colsum_n
       int* s_eo = s_cs + kMaxBN;                            // kI8: e_n
+      float* s_kf = reinterpret_cast<float*>(s_eo + kMaxBN);   // EPI_QKV: kfold of the column's channel
       for (int j = etid; j < p.bn; j += 32 * kEpiWarps) {
         const int n = ncol0 + j;
         float sc = 1.0f, bi = 0.0f;
@@ -314,6 +321,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         s_scale[j] = sc;
         s_bias[j] = bi;
+        if (kEpi == EPI_QKV && p.kfold != nullptr) s_kf[j] = n < p.n ? __ldg(p.kfold + n % p.d) : 1.0f;
         if (kEpi != EPI_PLAIN && (q2.mode == DGQ_Q_KWISE || q2.mode == DGQ_Q_SCALAR)) {
           // table slot j: EPI_QKV column j of the tile (index = channel inside the head);
           //               EPI_GEGLU output feature j of the tile (bn / 2 of them)
@@ -437,17 +445,20 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             else uaq_lean_lh<false, 8>(x, dd, ii, lo, hi);
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[v * 8 + i] = out_u8 ? x[i] - lo[i] : x[i];   // lo = -zp
+
           }
         };
         const uint32_t t_acc = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
         uint8_t* stg8 = reinterpret_cast<uint8_t*>(stg);
         const bool scatter_t = kEpi == EPI_QKV && p.transpose;
+        const uint32_t ldk = (kEpi == EPI_QKV && p.k_split) ? 2u * p.dp : static_cast<uint32_t>(p.dp);   // K row stride
         epi_bar_sync<32 * kEpiWarps>();     // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         for (int c = c_begin; c < c_end; ++c) {
           const int j0 = c * kUnit;         // first accumulator column of this unit inside the tile
           uint32_t hp[16];                  // 32 results of this thread's row, fp16 pairs
+          uint32_t hl[kEpi == EPI_QKV ? 16 : 1];   // EPI_QKV k_split: their low parts
 #pragma unroll
           for (int sb = 0; sb < 2; ++sb) {
             float g[16];
@@ -467,6 +478,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               tc_wait_ld();
               affine16(r1, j0 + sb * 16, g);
               fused_quant16(g, j0 + sb * 16);
+              if (kEpi == EPI_QKV && p.kfold != nullptr) {   // K operand: the Q quantizer's per-channel delta
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                  const float4 f = *reinterpret_cast<const float4*>(s_kf + j0 + sb * 16 + v * 4);
+                  g[v * 4 + 0] *= f.x; g[v * 4 + 1] *= f.y; g[v * 4 + 2] *= f.z; g[v * 4 + 3] *= f.w;
+                }
+              }
             }
             if (scatter_t) {
               // V^T [b, heads, dp, tp]: for a fixed column the 32 lanes hold 32 consecutive tokens
@@ -485,8 +503,19 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               for (int i = 0; i < 8; ++i) {
                 const __half2 h = __floats2half2_rn(g[2 * i], g[2 * i + 1]);
                 hp[sb * 8 + i] = *reinterpret_cast<const uint32_t*>(&h);
+                if (kEpi == EPI_QKV && p.k_split) {          // lo = fp16(value - fp16(value)): the next 11 bits
+                  const float2 hf = __half22float2(h);
+                  const __half2 l = __floats2half2_rn(g[2 * i] - hf.x, g[2 * i + 1] - hf.y);
+                  hl[sb * 8 + i] = *reinterpret_cast<const uint32_t*>(&l);
+                }
               }
             }
+          }
+          const int n_parts = (kEpi == EPI_QKV && p.k_split && !scatter_t) ? 2 : 1;
+          for (int part = 0; part < n_parts; ++part) {
+          if (part == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hp[i] = hl[i];
           }
           if (!scatter_t) {
             // row `lane`, 16-byte chunk v -> slot v ^ ((lane >> 1) & 3): conflict-free for the row-wise writes
@@ -511,13 +540,13 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 int gb = wbat;
                 gt = wtok + rl0;
                 while (gt >= p.tokens) { gt -= p.tokens; ++gb; }
-                o = (static_cast<uint32_t>(gb * p.heads + hh) * p.tokens + gt) * p.dp + dd;
-                row_step = 4u * p.dp;
+                o = (static_cast<uint32_t>(gb * p.heads + hh) * p.tokens + gt) * ldk + dd + part * p.dp;
+                row_step = 4u * ldk;
               } else {
                 o = static_cast<uint32_t>(warp_row0 + rl0) * p.ldc + n;
                 row_step = 4u * p.ldc;
               }
-              const uint32_t wrap_step = kEpi == EPI_QKV ? static_cast<uint32_t>(p.heads - 1) * p.tokens * p.dp : 0u;
+              const uint32_t wrap_step = kEpi == EPI_QKV ? static_cast<uint32_t>(p.heads - 1) * p.tokens * ldk : 0u;
 #pragma unroll
               for (int rr = 0; rr < 8; ++rr) {
                 const int rl = rr * 4 + rl0;
@@ -534,6 +563,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               }
             }
             __syncwarp();
+          }
           }
         }
         tc_fence_before();
@@ -800,7 +830,7 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
     DGQ_CHECK_ARG(q.mode >= DGQ_Q_NONE && q.mode <= DGQ_Q_ROWWISE);
     DGQ_CHECK_ARG(q.mode == DGQ_Q_NONE || (q.delta != nullptr && q.zp != nullptr));
     DGQ_CHECK_ARG(q.mode != DGQ_Q_ROWWISE || q.period > 0);
-    DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE) && q.emit_int >= 0 && q.emit_int <= 2);
+    DGQ_CHECK_ARG(!(q.emit_int && q.mode == DGQ_Q_KWISE && a->epi != DGQ_EPI_QKV) && q.emit_int >= 0 && q.emit_int <= 2);
     DGQ_CHECK_ARG(q.emit_int != 2 || (a->epi == DGQ_EPI_GEGLU && q.mode != DGQ_Q_NONE));
   }
   if (a->epi == DGQ_EPI_GEGLU) DGQ_CHECK_ARG(a->n % 64 == 0 && a->ldc >= a->n / 2 && static_cast<int64_t>(a->m) * a->ldc < (int64_t(1) << 31));
@@ -808,7 +838,8 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
     DGQ_CHECK_ARG(a->heads > 0 && a->d > 0 && a->d % 8 == 0 && a->dp >= a->d && a->dp % 8 == 0);
     DGQ_CHECK_ARG(a->n == a->heads * a->d && a->tokens > 0 && a->m % a->tokens == 0);
     DGQ_CHECK_ARG(!a->transpose || (a->tp >= a->tokens && a->tp % 8 == 0));
-    DGQ_CHECK_ARG(a->tokens >= 4 && static_cast<int64_t>(a->m) * a->heads * a->dp < (int64_t(1) << 31));
+    DGQ_CHECK_ARG(a->tokens >= 4 && static_cast<int64_t>(a->m) * a->heads * a->dp * (a->k_split ? 2 : 1) < (int64_t(1) << 31));
+    DGQ_CHECK_ARG(!(a->k_split && a->transpose));
   }
 
   static int force_ctas = -1;   // DGQ_GEMM_CTAS=1|2 pins the variant (benchmarking); default: by problem size
@@ -842,6 +873,7 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
   p.q2 = EpiQuant{a->q2.delta, a->q2.zp, a->q2.mode, a->q2.period > 0 ? a->q2.period : 1, a->q2.qmax, a->q2.emit_int};
   p.heads = a->heads; p.d = a->d > 0 ? a->d : 1; p.dp = a->dp; p.tokens = a->tokens > 0 ? a->tokens : 1;
   p.tp = a->tp; p.transpose = a->transpose; p.skip_first = a->skip_first;
+  p.kfold = a->epi == DGQ_EPI_QKV ? a->kfold : nullptr; p.k_split = a->epi == DGQ_EPI_QKV ? a->k_split : 0;
   p.colsum = i8 ? a->colsum : nullptr; p.b_off = i8 ? a->b_off : nullptr; p.row_zp = i8 ? a->row_zp : nullptr;
 
   CUtensorMap ta, tb;

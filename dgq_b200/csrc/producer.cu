@@ -694,9 +694,11 @@ __global__ void __launch_bounds__(256) geglu_quant_kernel(const TIn* __restrict_
 template <typename TIn>
 __global__ void __launch_bounds__(256) qkv_pack_kernel(const TIn* __restrict__ x, int ldx, int b, int t,
                                                        int heads, int d, int dp, int tp, int transpose,
-                                                       int skip_first, const QuantDev q, __half* __restrict__ out) {
+                                                       int skip_first, const QuantDev q, const float* __restrict__ kfold,
+                                                       int k_split, __half* __restrict__ out) {
   if (!transpose) {
     const int dvec = dp >> 3;
+    const int ldk = k_split ? 2 * dp : dp;
     const int64_t total = static_cast<int64_t>(b) * heads * t * dvec;
     for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
          idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -709,16 +711,31 @@ __global__ void __launch_bounds__(256) qkv_pack_kernel(const TIn* __restrict__ x
       if (d0 < d) {
         load8(x + (static_cast<size_t>(bb) * t + tt) * ldx + hh * d + d0, v);
         if (!(skip_first && tt == 0)) {
-          // KWISE index = d, ROWWISE index = token (minus the bypassed start token)
+          // KWISE index = d, ROWWISE index = token (minus the bypassed start token); emit_int: the bare integer
+          // code - zp in every mode (the scale is applied by the attention kernel / folded into K)
           QuantDev qq = q;
           if (qq.mode == DGQ_Q_ROWWISE) qq.period = 1 << 30;
           quant8(qq, v, d0, tt - skip_first, nullptr);
+        }
+        if (kfold != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= __ldg(kfold + d0 + i);
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       }
-      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(bb) * heads + hh) * t + tt) * dp + d0) = pack8(v);
+      __half* dst = out + ((static_cast<size_t>(bb) * heads + hh) * t + tt) * ldk + d0;
+      const uint4 hi = pack8(v);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      if (k_split) {
+        Half8 h;
+        h.u = hi;
+        float lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = v[i] - __half2float(h.h[i]);
+        *reinterpret_cast<uint4*>(dst + dp) = pack8(lo);
+      }
     }
   } else {
     const int tvec = tp >> 3;
@@ -992,10 +1009,13 @@ extern "C" int dgq_geglu_quant(const void* x, int src_is_f32, int m, int f, dgq_
 }
 
 extern "C" int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t, int heads, int d, int dp, int tp,
-                            int transpose, int skip_first, dgq_quant_t q, void* out, void* stream) {
+                            int transpose, int skip_first, dgq_quant_t q, const float* kfold, int k_split, void* out,
+                            void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && b > 0 && t > 0 && heads > 0 && d > 0);
-  DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && quant_ok(q) && !q.emit_int);
+  DGQ_CHECK_ARG(d % 8 == 0 && dp >= d && dp % 8 == 0 && ldx % 8 == 0 && q.emit_int >= 0 && q.emit_int <= 1);
+  DGQ_CHECK_ARG(q.mode >= DGQ_Q_NONE && q.mode <= DGQ_Q_ROWWISE && (q.mode == DGQ_Q_NONE || (q.delta != nullptr && q.zp != nullptr)));
+  DGQ_CHECK_ARG(!(transpose && (k_split || kfold != nullptr || q.emit_int)));
   DGQ_CHECK_ARG(!transpose || (tp >= t && tp % 8 == 0));
   const int64_t total = transpose ? static_cast<int64_t>(b) * heads * dp * (tp / 8)
                                   : static_cast<int64_t>(b) * heads * t * (dp / 8);
@@ -1003,10 +1023,10 @@ extern "C" int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (src_is_f32)
     qkv_pack_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), ldx, b, t, heads, d, dp, tp, transpose,
-                                                skip_first, to_dev(q), static_cast<__half*>(out));
+                                                skip_first, to_dev(q), kfold, k_split, static_cast<__half*>(out));
   else
     qkv_pack_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), ldx, b, t, heads, d, dp, tp,
-                                                 transpose, skip_first, to_dev(q), static_cast<__half*>(out));
+                                                 transpose, skip_first, to_dev(q), kfold, k_split, static_cast<__half*>(out));
   DGQ_RETURN_LAST_ERROR();
 }
 

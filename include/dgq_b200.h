@@ -170,6 +170,13 @@ typedef struct {
   int epi;             /* DGQ_EPI_* */
   dgq_quant_t q2;
   int heads, d, dp, tokens, tp, transpose, skip_first;
+  /* ---- DGQ_EPI_QKV producing the K operand of dgq_attention (k_split = 1): the value
+   *      kfold[channel] * aqtizer_k(k) is written as an fp16 (hi | lo) pair, out = [b, heads, tokens, 2 dp] with hi
+   *      at columns 0..dp-1 and lo = fp16(value - hi) at dp..2dp-1.  kfold = the per-channel delta of aqtizer_q when
+   *      that quantizer is K-wise (the Q operand is then the bare integer code - zp: q2.emit_int = 1 is accepted for
+   *      every q2.mode under DGQ_EPI_QKV), or NULL.                                                            */
+  const float* kfold;
+  int k_split;
   /* ---- dgq_gemm_i8 only (ignored by dgq_gemm_f16): integer zero-point corrections, see below */
   const int32_t* colsum; /* [n] sum_k B[n, k] (dgq_weight_to_i8)                                     */
   const int32_t* b_off;  /* [n] e_n = (offset subtracted from the weight codes) - (weight zero point),
@@ -205,9 +212,12 @@ int dgq_weight_to_i8(const uint8_t* codes, const float* zp, int n, int n_pad, in
  *   transpose == 0: out fp16 [b, heads, t, dp]         (Q and K)
  *   transpose == 1: out fp16 [b, heads, dp, tp]        (V^T), tp = round_up(t, 8)
  *   q.mode: NONE / SCALAR / KWISE (index d) / ROWWISE (index t - skip_first).
- *   skip_first == 1: token 0 bypasses the quantizer (start-peak, sd.py:176-180).               */
+ *   skip_first == 1: token 0 bypasses the quantizer (start-peak, sd.py:176-180).
+ *   q.emit_int = 1 (Q): the bare integer code - zp in every mode.  kfold / k_split (K): as DGQ_EPI_QKV --
+ *   value * kfold[channel] written as an fp16 (hi | lo) pair, out = [b, heads, t, 2 dp].                       */
 int dgq_qkv_pack(const void* x, int src_is_f32, int ldx, int b, int t, int heads, int d, int dp, int tp,
-                 int transpose, int skip_first, dgq_quant_t q, void* out, void* stream);
+                 int transpose, int skip_first, dgq_quant_t q, const float* kfold, int k_split, void* out,
+                 void* stream);
 
 #define DGQ_MAP_NONE 0    /* use_aq off: plain softmax                                   */
 #define DGQ_MAP_UNIFORM 1 /* UniformAffineQuantizer, always_zero (zp = 0)                */
@@ -232,7 +242,13 @@ typedef struct {
   uint8_t* codes;       /* optional u8 [b, heads, t, s]: integer codes of the map (verification only) */
   dgq_quant_t out_q;    /* quantizer of the consuming QuantLayer (to_out[0], quant/quant_layer.py:640-641)
                            applied to O before the store: KWISE index = column, ROWWISE = row % period;
-                           mode NONE: O is stored as is */
+                           mode NONE: O is stored as is; emit_int = 2: u8 codes (ldo in bytes) */
+  /* score operands in exact form (sd.py:171-183: q_hat . k_hat): q holds the bare integers code - zp of aqtizer_q
+   * and q_scale[token % q_scale_period] its scalar / per-token delta (NULL: none, or folded into k); k_split = 1:
+   * k is [b, heads, s, 2 dp] = fp16 (hi | lo) of the fully scaled key (dgq_gemm_t.k_split), dp <= 128.          */
+  const float* q_scale;
+  int q_scale_period;
+  int k_split;
 } dgq_attn_t;
 int dgq_attention(const dgq_attn_t* host_args, void* stream);
 
