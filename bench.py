@@ -322,6 +322,18 @@ def sd_loop_parity(torch, cfg, qnn, dev, lat, ctx):
         return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
 
+def shard_plan(total, world, rank, mb_max):
+    """micro-batch sizes rank `rank` runs for a total prompt batch sharded contiguously over `world` ranks
+    (src/gen4eval_SDXL.py:116: file_list[rank*len//ws : (rank+1)*len//ws]); fewer prompts than ranks: the first
+    `total` ranks take one each."""
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    share, mbs = hi - lo, []
+    while share > 0:
+        mbs.append(min(mb_max, share))
+        share -= mbs[-1]
+    return mbs
+
+
 def setup_sweep(torch, dist, cfg, qnn, dev, rank, world, extra, timed):
     """config 5: the reference's only multi-GPU pattern (src/gen4eval_SDXL.py:116: file_list[rank*len//ws : ...]):
     a FIXED total prompt batch sharded contiguously over the ranks (strong scaling), micro-batches of <= 16.
@@ -330,13 +342,7 @@ def setup_sweep(torch, dist, cfg, qnn, dev, rank, world, extra, timed):
     pools = {}
 
     def plan(total):
-        share = total // world if total >= world else (1 if rank < total else 0)
-        mbs = []
-        left = share
-        while left > 0:
-            mbs.append(min(mb_max, left))
-            left -= mbs[-1]
-        return mbs
+        return shard_plan(total, world, rank, mb_max)
 
     def inputs_for(mb, seed, pin=False):
         key = (mb, seed, pin)

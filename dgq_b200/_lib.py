@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "_C", "libdgq_b200.so")
 SYMBOLS = [
     "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight", "dgq_unpack_weight",
     "dgq_act_producer", "dgq_gn_stats", "dgq_ln_quant", "dgq_row_quant", "dgq_geglu_quant",
-    "dgq_gemm_f16", "dgq_gemm_i8", "dgq_weight_to_i8", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
+    "dgq_gemm_f16", "dgq_gemm_i8", "dgq_weight_to_i8", "dgq_conv_oob_colsum", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
     "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add", "dgq_sampler_step",
 ]
 
@@ -42,7 +42,10 @@ class GemmT(C.Structure):
                 ("out", C.c_void_p), ("ldc", C.c_int), ("out_f32", C.c_void_p), ("ep_is_f32", C.c_int),
                 ("epi", C.c_int), ("q2", QuantT), ("heads", C.c_int), ("d", C.c_int), ("dp", C.c_int),
                 ("tokens", C.c_int), ("tp", C.c_int), ("transpose", C.c_int), ("skip_first", C.c_int),
-                ("colsum", C.c_void_p), ("b_off", C.c_void_p), ("row_zp", C.c_void_p)]
+                ("kfold", C.c_void_p), ("k_split", C.c_int),
+                ("colsum", C.c_void_p), ("b_off", C.c_void_p), ("row_zp", C.c_void_p),
+                ("conv_b", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_c", C.c_int),
+                ("conv_csoob", C.c_void_p), ("conv_ldoob", C.c_int)]
 
 
 class AttnT(C.Structure):
@@ -52,7 +55,7 @@ class AttnT(C.Structure):
                 ("start_peak", C.c_int), ("delta", C.c_void_p), ("qmax", C.c_float),
                 ("row_max", C.c_void_p), ("row_sum", C.c_void_p), ("gmax", C.c_void_p),
                 ("out", C.c_void_p), ("ldo", C.c_int), ("out_is_f32", C.c_int), ("codes", C.c_void_p),
-                ("out_q", QuantT)]
+                ("out_q", QuantT), ("q_scale", C.c_void_p), ("q_scale_period", C.c_int), ("k_split", C.c_int)]
 
 
 class SamplerStepT(C.Structure):
@@ -89,7 +92,8 @@ def lib() -> C.CDLL:
             "dgq_gemm_f16": [C.POINTER(GemmT), vp],
             "dgq_gemm_i8": [C.POINTER(GemmT), vp],
             "dgq_weight_to_i8": [vp, vp, i, i, i, f, vp, vp, vp, vp],
-            "dgq_qkv_pack": [vp, i, i, i, i, i, i, i, i, i, i, QuantT, vp, vp],
+            "dgq_conv_oob_colsum": [vp, i, i, vp, vp],
+            "dgq_qkv_pack": [vp, i, i, i, i, i, i, i, i, i, i, QuantT, vp, i, vp, vp],
             "dgq_attention": [C.POINTER(AttnT), vp],
             "dgq_timestep_embedding": [vp, i, i, vp, vp, i, vp],
             "dgq_nchw_to_nhwc": [vp, i, i, i, i, vp, i, vp],

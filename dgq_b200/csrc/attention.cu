@@ -180,13 +180,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int dchunks = p.dp >> 6;
   const uint32_t q_bytes = dchunks * kChunkBytes;          // one Q tile
-  const uint32_t k_bytes = p.k_split ? 2 * q_bytes : q_bytes;   // one K stage: hi chunks, then lo chunks
-  const int kchunks = p.k_split ? 2 * dchunks : dchunks;
+  const int kparts = p.k_split ? 2 : 1;                    // a K tile travels as `kparts` ring entries: hi, then lo
   const uint32_t v_stage = 2 * p.dp * 128;                 // two [dp x 64] sub-tiles
   const uint32_t nqb = p.nq_buf, nkb = p.nk_buf, nvb = p.nv_buf, nob = p.no_buf, nh = p.nh;
   uint8_t* s_q = smem;
   uint8_t* s_k = s_q + nqb * q_bytes;
-  uint8_t* s_v = s_k + nkb * k_bytes;
+  uint8_t* s_v = s_k + nkb * q_bytes;
   uint8_t* s_p = s_v + (PASS == 2 ? nvb * v_stage : 0);
   uint8_t* s_end = s_p + (PASS == 2 ? 2 * 2 * kChunkBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_end);
@@ -236,12 +235,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tma_load_3d(s_q + qb * q_bytes + c * kChunkBytes, &tm_q, &bars[B_QFULL + qb], c * 64,
                         (qg * static_cast<int>(nh) + static_cast<int>(h)) * kTileQ, bh);
         }
-        for (int j = 0; j < p.nkv; ++j, ++g) {
-          const uint32_t slot = g % nkb;
-          mbar_wait(&bars[B_KEMPTY + slot], ((g / nkb) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[B_KFULL + slot], k_bytes);
-          for (int c = 0; c < kchunks; ++c)
-            tma_load_3d(s_k + slot * k_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], c * 64, j * kTileK, bh);
+        for (int j = 0; j < p.nkv; ++j) {
+          for (int part = 0; part < kparts; ++part, ++g) {     // g counts ring entries here
+            const uint32_t slot = g % nkb;
+            mbar_wait(&bars[B_KEMPTY + slot], ((g / nkb) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
+            for (int c = 0; c < dchunks; ++c)
+              tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], (part * dchunks + c) * 64,
+                          j * kTileK, bh);
+          }
         }
       }
     }
@@ -300,25 +302,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileK);
       uint32_t u = 0, g = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        for (int j = 0; j < p.nkv; ++j, ++g) {
-          const uint32_t slot = g % nkb;
-          mbar_wait(&bars[B_KFULL + slot], (g / nkb) & 1);
-          for (uint32_t h = 0; h < nh; ++h, ++u) {
-            const uint32_t qn = it * nh + h, qb = qn % nqb, sb = u & 1;
-            if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
-            mbar_wait(&bars[B_SEMPTY + sb], ((u >> 1) & 1) ^ 1);
-            tc_fence_after();
-            for (int c = 0; c < kchunks; ++c) {    // Q . K_hi, then Q . K_lo into the same accumulator
-              const int cq = c < dchunks ? c : c - dchunks;
-              const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + cq * kChunkBytes));
-              const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * k_bytes + c * kChunkBytes));
+        for (int j = 0; j < p.nkv; ++j, ++g, u += nh) {
+          // S(u + h) = Q_h . K_hi (+ Q_h . K_lo): the parts arrive as separate ring entries, so the lo part of a tile
+          // can share its buffer with the hi part when shared memory is short (dp = 128 / 192)
+          for (int part = 0; part < kparts; ++part) {
+            const uint32_t gp = g * kparts + part, slot = gp % nkb;
+            mbar_wait(&bars[B_KFULL + slot], (gp / nkb) & 1);
+            for (uint32_t h = 0; h < nh; ++h) {
+              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu & 1;
+              if (part == 0) {
+                if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
+                mbar_wait(&bars[B_SEMPTY + sb], ((uu >> 1) & 1) ^ 1);
+              }
+              tc_fence_after();
+              for (int c = 0; c < dchunks; ++c) {
+                const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + c * kChunkBytes));
+                const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * q_bytes + c * kChunkBytes));
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (c | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks)
+                  tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (part | c | ks) != 0 ? 1u : 0u);
+              }
+              if (part == kparts - 1) {
+                tc_commit(&bars[B_SFULL + sb]);
+                if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);       // last read of this Q tile
+              }
+              if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this ring entry
             }
-            tc_commit(&bars[B_SFULL + sb]);
-            if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this K tile
-            if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);         // last read of this Q tile
           }
         }
       }
@@ -739,7 +748,6 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   DGQ_CHECK_ARG(a->out_q.mode >= DGQ_Q_NONE && a->out_q.mode <= DGQ_Q_ROWWISE);
   DGQ_CHECK_ARG(a->out_q.mode == DGQ_Q_NONE || (a->out_q.delta != nullptr && a->out_q.zp != nullptr));
   DGQ_CHECK_ARG(!(a->out_q.emit_int && a->out_q.mode == DGQ_Q_KWISE));
-  DGQ_CHECK_ARG(!(a->k_split && a->dp > 128));           // shared memory: dp = 192 has no room for the lo tiles
   DGQ_CHECK_ARG(a->q_scale == nullptr || a->q_scale_period > 0);
   DGQ_CHECK_ARG(a->out_q.emit_int != 2 || (a->out_q.mode != DGQ_Q_NONE && !a->out_is_f32 && a->ldo % 16 == 0));
 
@@ -753,16 +761,18 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   p.q_tiles = (a->t + kTileQ - 1) / kTileQ;
   p.k_split = a->k_split ? 1 : 0;
   p.q_scale = a->q_scale; p.q_period = a->q_scale_period > 0 ? a->q_scale_period : 1;
+  p.nh = (a->dp <= 128 && p.q_tiles > 1) ? 2 : 1;
   if (!p.k_split) {
-    p.nh = (a->dp <= 128 && p.q_tiles > 1) ? 2 : 1;
     p.nq_buf = a->dp <= 64 ? 4 : (a->dp <= 128 ? 2 : 1);
     p.nk_buf = a->dp <= 64 ? 3 : 1;
-    p.nv_buf = a->dp <= 64 ? 2 : 1;
-  } else {     // K stages are twice as large (hi | lo): dp = 64: Q 2 + K 2 x 2 + V 2 + P' 4 (16 KB units) = 192 KB
-    p.nh = (a->dp <= 64 && p.q_tiles > 1) ? 2 : 1;
-    p.nq_buf = a->dp <= 64 ? 2 : 1;
-    p.nk_buf = a->dp <= 64 ? 2 : 1;
-    p.nv_buf = a->dp <= 64 ? 2 : 1;
+  } else {     // K tiles travel as two ring entries (hi, lo) of one Q-tile size each; dp > 64: hi and lo share one buffer
+    p.nq_buf = a->dp <= 128 ? 2 : 1;
+    p.nk_buf = a->dp <= 64 ? 4 : 1;
+  }
+  p.nv_buf = a->dp <= 64 ? 2 : 1;
+  if (p.k_split && a->dp <= 64 && p.nkv == 1) {   // cross-attention: one K/V tile per item, latency-bound -- spend
+    p.nq_buf = 4;                                   // the shared memory on the NEXT item's Q tiles (16 KB units:
+    p.nv_buf = 1;                                   // Q 4 + K 4 + V 1 + P' 4 = 208 KB)
   }
   p.no_buf = a->dp <= 128 ? 2 : 1;
   p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
@@ -786,12 +796,11 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   if (rc != 0) return rc;
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
-  const uint32_t k_bytes = p.k_split ? 2 * q_bytes : q_bytes;
   const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 4 * 192 * 4 + 3 * 128 * 4 + 64;
   AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring
   if (p1.nq_buf > 2) p1.nq_buf = 2;
-  const uint32_t smem1 = q_bytes * p1.nq_buf + k_bytes * p1.nk_buf + tail;
-  const uint32_t smem2 = q_bytes * p.nq_buf + k_bytes * p.nk_buf + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
+  const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
+  const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
   KernelFn k1 = attention_kernel<1, 0, false, false>;
   KernelFn k2;

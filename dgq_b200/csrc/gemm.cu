@@ -28,6 +28,8 @@
 //   read each A stage from shared memory (dp4a), so no producer has to emit it.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -99,6 +101,14 @@ struct GemmDev {
   const int32_t* colsum;   // [n] sum_k B[n, k]
   const int32_t* b_off;    // [n] e_n = b_off_n - wz_n, or nullptr (= 0: the weight zero point is folded into B)
   const float* row_zp;     // activation zero point: row_zp[m % row_period]
+  // kI8 + EPI_PLAIN, implicit 3x3 / stride 1 / pad 1 convolution: A is the NHWC u8 code tensor [cv_b, cv_h, cv_w, cv_c]
+  // itself, read through a 4-D tensor map -- CTA tile = a (cv_bn x cv_bh x cv_bw) = 128-pixel patch, K block =
+  // (tap, 128 channels), out-of-image taps zero-filled by TMA.  An exact-zero padding tap means code = zero point,
+  // not code = 0, so the epilogue corrects per BORDER CLASS of the row (3 x 3: top / mid / bottom x left / mid /
+  // right): colsum_n loses cv_csoob[class][n] = the column sums of the taps that fell outside, K loses their count.
+  int cv_on, cv_b, cv_h, cv_w, cv_c, cv_bw, cv_bh, cv_bn, cv_cblocks, cv_lw, cv_lwh;
+  const int32_t* cv_csoob;
+  int cv_ldoob;
 };
 
 template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the epilogue warps only
@@ -140,7 +150,16 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
   const int worker = kCtas == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int workers = static_cast<int>(gridDim.x) / kCtas;
-  const int k_blocks = (p.k + kBKe - 1) / kBKe;
+  const bool cv = kI8 && kEpi == EPI_PLAIN && p.cv_on != 0;
+  const int k_blocks = cv ? 9 * p.cv_cblocks : (p.k + kBKe - 1) / kBKe;
+  // implicit conv: pixel patch of CTA `rank` of tile row m_blk -> (first x, first y, first image)
+  auto cv_origin = [&](int m_blk, int& px0, int& py0, int& b0) {
+    const int pidx = m_blk * kCtas + static_cast<int>(rank);
+    const int pw = p.cv_w >> p.cv_lw, ph = p.cv_h / p.cv_bh;
+    px0 = (pidx % pw) << p.cv_lw;
+    py0 = ((pidx / pw) % ph) * p.cv_bh;
+    b0 = (pidx / (pw * ph)) * p.cv_bn;
+  };
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int b_rows = p.bn / kCtas;             // rows of B staged by this CTA
 
@@ -177,9 +196,23 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
         const int row_a = m_blk * (kBM * kCtas) + static_cast<int>(rank) * kBM;
         const int row_b = n_blk * p.bn + static_cast<int>(rank) * b_rows;
+        int px0 = 0, py0 = 0, b0 = 0;
+        if (cv) cv_origin(m_blk, px0, py0, b0);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (kCtas == 1) {
+          if (cv) {
+            const int tap = kb / p.cv_cblocks, ka = (kb - tap * p.cv_cblocks) * kBKe;
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            if (kCtas == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma_load_4d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], ka, px0 + dx, py0 + dy, b0);
+              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], tap * p.cv_c + ka, row_b);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+              tma_load_4d_pair(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], ka, px0 + dx, py0 + dy, b0);
+              tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], tap * p.cv_c + ka, row_b);
+            }
+          } else if (kCtas == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
             tma_load_2d(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBKe, row_a);
             tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBKe, row_b);
@@ -291,8 +324,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
       const int tile_row0 = m_blk * (kBM * kCtas) + static_cast<int>(rank) * kBM;
       const int warp_row0 = tile_row0 + quad * 32;
-      const int row = warp_row0 + lane;
-      const bool row_ok = row < p.m;
+      int px0 = 0, py0 = 0, b0 = 0;
+      if (cv) cv_origin(m_blk, px0, py0, b0);
+      // implicit conv: row r of this CTA's tile -> output row (or -1 beyond the batch) and its border class
+      auto cv_row = [&](int r, int& cls) -> int {
+        const int x = px0 + (r & (p.cv_bw - 1)), y = py0 + ((r >> p.cv_lw) & (p.cv_bh - 1)), bb = b0 + (r >> p.cv_lwh);
+        cls = (y == 0 ? 0 : (y == p.cv_h - 1 ? 6 : 3)) + (x == 0 ? 0 : (x == p.cv_w - 1 ? 2 : 1));
+        return bb < p.cv_b ? (bb * p.cv_h + y) * p.cv_w + x : -1;
+      };
+      int my_cls = 4;
+      const int row = cv ? cv_row(quad * 32 + lane, my_cls) : warp_row0 + lane;
+      const bool row_ok = cv ? row >= 0 : row < p.m;
       const int ncol0 = n_blk * p.bn;
       float* s_scale = s_epi + (it & 1) * kEpiTab * kMaxBN;
       float* s_bias = s_scale + kMaxBN;
@@ -313,8 +355,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (n < p.n) {
           if (p.scale != nullptr) sc = __ldg(p.scale + n);
           if (p.bias != nullptr) bi = __ldg(p.bias + n);
-          if (temb_tile && tile_row0 < p.m) {
-            const size_t off = static_cast<size_t>(tile_row0 / p.rows_per_batch) * p.ld_temb + n;
+          if (temb_tile && (cv ? b0 < p.cv_b : tile_row0 < p.m)) {
+            const size_t off = static_cast<size_t>(cv ? b0 : tile_row0 / p.rows_per_batch) * p.ld_temb + n;
             bi += p.ep_is_f32 ? __ldg(static_cast<const float*>(p.temb) + off)
                               : __half2float(static_cast<const __half*>(p.temb)[off]);
           }
@@ -339,9 +381,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           s_qh[j] = __fsub_rn(q2.qmax, zz);
         }
       }
-      const char* temb_row = (p.temb != nullptr && !temb_tile && row_ok)
-                                 ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
-                                 : nullptr;
       const float rs = (p.row_scale != nullptr && row_ok) ? __ldg(p.row_scale + (row % p.row_period)) : 1.0f;
       // kI8: integer correction terms of this thread's row: -za and (rowsum - K * za)
       int nrz = 0, rsp = 0;
@@ -574,127 +613,126 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
-      float4 t_cur[8], t_nxt[8];
-      auto load_resid = [&](int c, float4 (&t)[8]) {
-        const int n = ncol0 + c * 32 + cq;
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int grow = warp_row0 + rr * 4 + rl0;
-          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (grow < p.m && n < p.n) {
-            if (p.ep_is_f32) {
-              u = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
-            } else {
-              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
-              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-              u = make_float4(lo.x, lo.y, hi.x, hi.y);
-            }
-          }
-          t[rr] = u;
-        }
-      };
-      const bool has_resid = kEpi == EPI_PLAIN && p.resid != nullptr;
+      // ---- plain epilogue.  Phase A (thread = row) only moves the raw accumulator chunk TMEM -> registers -> the
+      // warp's padded smem tile.  Phase B (lane = 4 columns x every 4th row) does the arithmetic with ITS columns'
+      // constants held in registers for the whole chunk and its 8 rows' constants for the whole tile -- the affine,
+      // the kind::i8 integer zero-point corrections, + residual -- and stores 128-byte (fp32) / 64-byte (fp16) row
+      // segments.  (Round 1 did the affine in phase A: every thread re-read every column's constants from shared
+      // memory, 2-4 LDS per result; ncu showed the kind::i8 kernel bound there, profiles/r2_gemm_i8_vs_f16.txt.)
+      const bool has_resid = p.resid != nullptr;
+      const bool has_rs = p.row_scale != nullptr;
       const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
-      // ---- lean path of the fp32 residual stream (the hot case: every to_out / ff.net.2 / conv2 / proj_out
-      // layer): full tile, fp32 result (+ fp32 residual), bias / temb already folded into the staged tables.
-      // No per-element bounds or dtype branches; the next accumulator chunk is requested as soon as the
-      // current one is in registers.
-      if (kEpi == EPI_PLAIN && p.out == nullptr && (p.ep_is_f32 || (p.resid == nullptr && p.temb == nullptr)) &&
-          temb_row == nullptr && tile_row0 + kBM <= p.m && ncol0 + p.bn <= p.n && c_begin < c_end) {
-        const float* resid = static_cast<const float*>(p.resid);
-        const size_t row_a = static_cast<size_t>(warp_row0 + rl0);
+      // row constants (activation delta, -zero point, row sum - K * zero point) live in the 4 pad columns of the
+      // row's staging line: written once per tile by the row's own thread, read back by whichever lane finishes it
+      {
+        const int ri = ((has_rs || kI8) && row_ok) ? row % p.row_period : 0;
+        const float ra = (has_rs && row_ok) ? __ldg(p.row_scale + ri) : 1.0f;
+        int nz = 0, rp = 0;
+        if (kI8) {
+          const int za = row_ok ? static_cast<int>(__ldg(p.row_zp + ri)) : 0;
+          nz = -za;
+          // K of this row: implicit conv rows at the image border see fewer taps
+          const int cy = my_cls / 3, cx = my_cls - cy * 3;
+          const int kin = cv ? p.cv_c * ((cy == 1 ? 3 : 2) * (cx == 1 ? 3 : 2)) : p.k;
+          if (need_rowsum) rp = s_rowsum[(it % kRsRing) * kBM + quad * 32 + lane] - kin * za;
+        }
+        *reinterpret_cast<uint4*>(stg + lane * kStgLd + 32) =
+            make_uint4(__float_as_uint(ra), static_cast<uint32_t>(nz), static_cast<uint32_t>(rp), static_cast<uint32_t>(my_cls));
+      }
+      auto plain = [&](auto full_tag) {
+        constexpr bool kFullTile = decltype(full_tag)::value;   // interior tile: no row / column bounds
+        float4 t_cur[8], t_nxt[8];
         auto ldres = [&](int c, float4 (&t)[8]) {
-          const float* b = resid + row_a * p.ld_resid + ncol0 + c * 32 + cq;
+          const int n = ncol0 + c * 32 + cq;
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) t[rr] = __ldg(reinterpret_cast<const float4*>(b + static_cast<size_t>(rr) * 4 * p.ld_resid));
+          for (int rr = 0; rr < 8; ++rr) {
+            int cls_unused;
+            const int grow = cv ? cv_row(quad * 32 + rr * 4 + rl0, cls_unused) : warp_row0 + rr * 4 + rl0;
+            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kFullTile || (grow >= 0 && grow < p.m && n < p.n)) {
+              if (p.ep_is_f32) {
+                u = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+              } else {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                u = make_float4(lo.x, lo.y, hi.x, hi.y);
+              }
+            }
+            t[rr] = u;
+          }
         };
-        if (has_resid) ldres(c_begin, t_cur);
-        epi_bar_sync<32 * kEpiWarps>();                     // staged tables visible
+        if (has_resid && c_begin < c_end) ldres(c_begin, t_cur);
+        epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         uint32_t r[32];
-        tmem_ld_32x32(t_row + c_begin * 32, r);
-        const bool has_rs = p.row_scale != nullptr;
+        if (c_begin < c_end) tmem_ld_32x32(t_row + c_begin * 32, r);
         for (int c = c_begin; c < c_end; ++c) {
           const int j0 = c * 32;
           if (has_resid && c + 1 < c_end) ldres(c + 1, t_nxt);
           tc_wait_ld();
-          float g[32];
-          if (has_rs || kI8) {
-            affine32(r, j0, g);
-          } else {
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
-              const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
-              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]), sc.x, bi.x);
-              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]), sc.y, bi.y);
-              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]), sc.z, bi.z);
-              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]), sc.w, bi.w);
-            }
-          }
-          if (c + 1 < c_end) tmem_ld_32x32(t_row + j0 + 32, r);
 #pragma unroll
           for (int v = 0; v < 8; ++v)
-            *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+            *reinterpret_cast<uint4*>(stg + lane * kStgLd + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+          if (c + 1 < c_end) tmem_ld_32x32(t_row + j0 + 32, r);   // the next chunk travels while this one is finished
           __syncwarp();
-          float* o = p.out_f32 + row_a * p.ldc + ncol0 + j0 + cq;
-#pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            float4 x = *reinterpret_cast<const float4*>(stg + (rr * 4 + rl0) * kStgLd + cq);
-            if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
-            *reinterpret_cast<float4*>(o + static_cast<size_t>(rr) * 4 * p.ldc) = x;
+          const int j = j0 + cq;                                  // this lane's 4 columns inside the tile
+          const int n = ncol0 + j;
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + j);
+          const float4 bi = *reinterpret_cast<const float4*>(s_bias + j);
+          int4 cs = make_int4(0, 0, 0, 0), eo = make_int4(0, 0, 0, 0);
+          if (kI8) {
+            cs = *reinterpret_cast<const int4*>(s_cs + j);
+            eo = *reinterpret_cast<const int4*>(s_eo + j);
           }
-          __syncwarp();
-          if (has_resid) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-      // ---- general plain path: edge tiles, fp16 results, per-row time-embedding rows
-      if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
-      epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t r[32];
-        const int j0 = c * kUnit;           // first accumulator column of this iteration inside the tile
-        tmem_ld_32x32(t_row + j0, r);
-        if (has_resid && c + 1 < c_end) load_resid(c + 1, t_nxt);
-        float g[32];                        // this thread's row, 32 result columns
-        tc_wait_ld();
-        affine32(r, j0, g);
-        if (temb_row != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = ncol0 + j0 + i;
-            if (n < p.n)
-              g[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n]
-                                  : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < 8; ++v)
-          *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
-        __syncwarp();
-        const int n = ncol0 + j0 + cq;      // result column of this lane's 4 values
-        if (n < p.n) {
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
             const int rl = rr * 4 + rl0;
-            const int grow = warp_row0 + rl;
-            if (grow < p.m) {
-              float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
-              if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+            int cls = 4;
+            const int grow = cv ? cv_row(quad * 32 + rl, cls) : warp_row0 + rl;
+            const uint4 raw = *reinterpret_cast<const uint4*>(stg + rl * kStgLd + cq);
+            float4 x;
+            float ra = 1.0f;
+            if (kI8) {      // exact integer zero-point corrections, then one conversion
+              const uint4 rc = *reinterpret_cast<const uint4*>(stg + rl * kStgLd + 32);
+              ra = __uint_as_float(rc.x);
+              const int nz = static_cast<int>(rc.y), rp = static_cast<int>(rc.z);
+              int4 c4 = cs;
+              if (cv && cls != 4 && (kFullTile || n < p.n)) {   // border row: the out-of-image taps carry no weight
+                const int4 ob = __ldg(reinterpret_cast<const int4*>(p.cv_csoob + static_cast<size_t>(cls) * p.cv_ldoob + n));
+                c4.x -= ob.x; c4.y -= ob.y; c4.z -= ob.z; c4.w -= ob.w;
+              }
+              x.x = __int2float_rn(static_cast<int>(raw.x) + nz * c4.x + eo.x * rp);
+              x.y = __int2float_rn(static_cast<int>(raw.y) + nz * c4.y + eo.y * rp);
+              x.z = __int2float_rn(static_cast<int>(raw.z) + nz * c4.z + eo.z * rp);
+              x.w = __int2float_rn(static_cast<int>(raw.w) + nz * c4.w + eo.w * rp);
+            } else {
+              if (has_rs) ra = stg[rl * kStgLd + 32];
+              x = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
+            }
+            if (has_rs || kI8) {
+              x.x = fmaf(x.x * ra, sc.x, bi.x); x.y = fmaf(x.y * ra, sc.y, bi.y);
+              x.z = fmaf(x.z * ra, sc.z, bi.z); x.w = fmaf(x.w * ra, sc.w, bi.w);
+            } else {
+              x.x = fmaf(x.x, sc.x, bi.x); x.y = fmaf(x.y, sc.y, bi.y);
+              x.z = fmaf(x.z, sc.z, bi.z); x.w = fmaf(x.w, sc.w, bi.w);
+            }
+            const bool ok = kFullTile || (grow >= 0 && grow < p.m && n < p.n);
+            if (!kFullTile && p.temb != nullptr && !temb_tile && ok) {   // a tile that spans several samples
+              const size_t off = static_cast<size_t>(grow / p.rows_per_batch) * p.ld_temb + n;
+              if (p.ep_is_f32) {
+                const float4 te = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.temb) + off));
+                x.x += te.x; x.y += te.y; x.z += te.z; x.w += te.w;
+              } else {
+                const uint2 te = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.temb) + off));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&te.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&te.y));
+                x.x += lo.x; x.y += lo.y; x.z += hi.x; x.w += hi.y;
+              }
+            }
+            if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+            if (ok) {
               const size_t o = static_cast<size_t>(grow) * p.ldc + n;
               if (p.out != nullptr) {
                 const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
@@ -703,13 +741,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
               if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
             }
           }
-        }
-        __syncwarp();
-        if (has_resid) {
+          __syncwarp();
+          if (has_resid) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+            for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+          }
         }
-      }
+      };
+      // interior tiles with no per-row time-embedding rows take the branch-free instantiation
+      const bool rows_full = cv ? b0 + p.cv_bn <= p.cv_b : tile_row0 + kBM <= p.m;
+      if (rows_full && ncol0 + p.bn <= p.n && (p.temb == nullptr || temb_tile)) plain(std::true_type{});
+      else plain(std::false_type{});
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -756,6 +798,21 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
+}
+
+// u8 NHWC [b, h, w, c] (contiguous); box = [bn, bh, bw, 128 channels]: 128 pixel rows of 128 bytes, 128B swizzle
+int make_tmap_nhwc_u8(CUtensorMap* map, const void* ptr, uint64_t b, uint64_t h, uint64_t w, uint64_t c,
+                      uint32_t bn, uint32_t bh, uint32_t bw) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) return static_cast<int>(cudaErrorNotSupported);
+  cuuint64_t gdim[4] = {c, w, h, b};
+  cuuint64_t gstride[3] = {c, w * c, h * w * c};
+  cuuint32_t box[4] = {128, bw, bh, bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(cudaErrorInvalidValue);
@@ -820,6 +877,19 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
     DGQ_CHECK_ARG(a->k % 16 == 0 && a->lda % 16 == 0 && a->ldb % 16 == 0);
     DGQ_CHECK_ARG(a->colsum != nullptr && a->row_zp != nullptr && a->row_scale != nullptr);
   }
+  // implicit 3x3 convolution: patch geometry (bw x bh x bn = 128 pixels)
+  const bool conv = a->conv_h > 0;
+  int cv_bw = 0, cv_bh = 0, cv_bn = 0;
+  if (conv) {
+    DGQ_CHECK_ARG(i8 && a->epi == DGQ_EPI_PLAIN && a->conv_csoob != nullptr && a->conv_ldoob >= a->n);
+    DGQ_CHECK_ARG(a->conv_b > 0 && a->conv_w > 1 && a->conv_h > 1 && a->conv_c > 0 && a->conv_c % 16 == 0);
+    DGQ_CHECK_ARG(a->k == 9 * a->conv_c && a->m == a->conv_b * a->conv_h * a->conv_w && a->row_period == 1);
+    cv_bw = a->conv_w < 16 ? a->conv_w : 16;
+    cv_bh = a->conv_h < 128 / cv_bw ? a->conv_h : 128 / cv_bw;
+    cv_bn = 128 / (cv_bw * cv_bh);
+    DGQ_CHECK_ARG((cv_bw & (cv_bw - 1)) == 0 && (cv_bh & (cv_bh - 1)) == 0 && cv_bw * cv_bh * cv_bn == 128);
+    DGQ_CHECK_ARG(a->conv_w % cv_bw == 0 && a->conv_h % cv_bh == 0);
+  }
   DGQ_CHECK_ARG(a->out != nullptr || a->out_f32 != nullptr);
   DGQ_CHECK_ARG(a->temb == nullptr || (a->rows_per_batch > 0 && a->ld_temb % 8 == 0));
   DGQ_CHECK_ARG(a->resid == nullptr || a->ld_resid % 8 == 0);
@@ -875,10 +945,23 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
   p.tp = a->tp; p.transpose = a->transpose; p.skip_first = a->skip_first;
   p.kfold = a->epi == DGQ_EPI_QKV ? a->kfold : nullptr; p.k_split = a->epi == DGQ_EPI_QKV ? a->k_split : 0;
   p.colsum = i8 ? a->colsum : nullptr; p.b_off = i8 ? a->b_off : nullptr; p.row_zp = i8 ? a->row_zp : nullptr;
+  p.cv_on = conv ? 1 : 0;
+  p.cv_b = a->conv_b; p.cv_h = a->conv_h; p.cv_w = a->conv_w; p.cv_c = a->conv_c;
+  p.cv_bw = cv_bw; p.cv_bh = cv_bh; p.cv_bn = cv_bn;
+  p.cv_cblocks = conv ? (a->conv_c + 127) / 128 : 0;
+  p.cv_lw = 0; p.cv_lwh = 0;
+  while (conv && (1 << p.cv_lw) < cv_bw) ++p.cv_lw;
+  while (conv && (1 << p.cv_lwh) < cv_bw * cv_bh) ++p.cv_lwh;
+  p.cv_csoob = a->conv_csoob; p.cv_ldoob = a->conv_ldoob;
+  if (conv) {   // one CTA tile per 128-pixel patch (the last image group may be partial: rows beyond the batch are skipped)
+    const int patches = (a->conv_w / cv_bw) * (a->conv_h / cv_bh) * ((a->conv_b + cv_bn - 1) / cv_bn);
+    p.m_tiles = (patches + ctas - 1) / ctas;
+  }
 
   CUtensorMap ta, tb;
   const int esize = i8 ? 1 : 2;
-  int rc = make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM, esize);
+  int rc = conv ? make_tmap_nhwc_u8(&ta, a->a, a->conv_b, a->conv_h, a->conv_w, a->conv_c, cv_bn, cv_bh, cv_bw)
+                : make_tmap_2d(&ta, a->a, a->m, a->k, a->lda, kBM, esize);
   if (rc != 0) return rc;
   // B rows beyond n are zero-filled by TMA (out-of-bounds box rows)
   rc = make_tmap_2d(&tb, a->b, a->n, a->k, a->ldb, p.bn / ctas, esize);

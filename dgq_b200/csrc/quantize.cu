@@ -181,6 +181,32 @@ __global__ void weight_to_i8_kernel(const uint8_t* __restrict__ codes, const flo
   }
 }
 
+// one warp per output channel: per-tap sums of the s8 operand, folded into the 9 border classes
+__global__ void conv_oob_colsum_kernel(const int8_t* __restrict__ operand, int n_pad, int c, int32_t* __restrict__ csoob) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  int tap_sum[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    int s = 0;
+    for (int k = lane; k < c; k += 32) s += operand[static_cast<size_t>(row) * 9 * c + t * c + k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    tap_sum[t] = s;
+  }
+  if (lane < 9) {
+    const int cy = lane / 3, cx = lane % 3;       // class of the OUTPUT pixel: 0 = first row / column, 2 = last
+    int s = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const bool out = (cy == 0 && dy < 0) || (cy == 2 && dy > 0) || (cx == 0 && dx < 0) || (cx == 2 && dx > 0);
+      if (out) s += tap_sum[t];
+    }
+    csoob[lane * n_pad + row] = s;
+  }
+}
+
 static int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g < 1) g = 1;
@@ -259,5 +285,12 @@ extern "C" int dgq_weight_to_i8(const uint8_t* codes, const float* zp, int n, in
   DGQ_CHECK_ARG(n > 0 && n_pad >= n && k_out > 0 && qmax >= 1.0f && qmax <= 255.0f);
   weight_to_i8_kernel<<<(n_pad + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, zp, n, n_pad, k_out, qmax,
                                                                                    operand, colsum, b_off);
+  DGQ_RETURN_LAST_ERROR();
+}
+
+extern "C" int dgq_conv_oob_colsum(const int8_t* operand, int n_pad, int c, int32_t* csoob, void* stream) {
+  using namespace dgq;
+  DGQ_CHECK_ARG(operand != nullptr && csoob != nullptr && n_pad > 0 && c > 0);
+  conv_oob_colsum_kernel<<<(n_pad + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(operand, n_pad, c, csoob);
   DGQ_RETURN_LAST_ERROR();
 }

@@ -89,9 +89,27 @@ def _emit(ql, q: ops.QParam) -> int:
     return 2 if (USE_I8 and ql is not None and ql.i8_ok(q)) else 1
 
 
+# implicit-GEMM 3x3 convolution for per-tensor (scalar) activation scales on the kind::i8 path: the producer writes the
+# NHWC u8 codes ONCE ([M, C], what a 1x1 conv's producer writes) and the GEMM gathers the 9 taps itself through a 4-D
+# TMA map -- no 9x im2col matrix in HBM.  K-wise / row-wise group scales quantise the UNFOLDED view (reference
+# quant_layer.py:630-641: up to 9 different codes per input element), so they keep the im2col producer.
+IMPLICIT_CONV = os.environ.get("DGQ_IMPLICIT_CONV", "1") != "0"
+
+
+def _implicit_ok(ql, q: ops.QParam, h: int, w: int, k: int, s: int) -> bool:
+    if not (IMPLICIT_CONV and k == 3 and s == 1 and q.mode == ops.Q_SCALAR and not ql.pad_quantized):
+        return False
+    if _emit(ql, q) != 2 or h < 2 or w < 2:
+        return False
+    bw = min(w, 16)
+    bh = min(h, 128 // bw)
+    return (bw & (bw - 1)) == 0 and (bh & (bh - 1)) == 0 and w % bw == 0 and h % bh == 0 and 128 % (bw * bh) == 0
+
+
 def _gemm(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, temb=None, rows_per_batch=0, resid=None,
-          want_f32=None, **fused):
-    """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q` (u8 codes: kind::i8)."""
+          want_f32=None, conv_geom=None, **fused):
+    """qGEMM of QuantLayer `ql` on the operand its producer wrote under quantizer `q` (u8 codes: kind::i8).
+    conv_geom = (b, h, w, c): a_op is the NHWC code tensor of an implicit 3x3 convolution."""
     i8 = a_op.dtype == torch.uint8
     pack = ql.packed(geglu=fused.get("epi") == ops.EPI_GEGLU, i8=i8)
     operand, scale, bias, n_pad = pack[:4]
@@ -100,6 +118,8 @@ def _gemm(ql, a_op: torch.Tensor, q: ops.QParam = ops.NOQ, *, temb=None, rows_pe
     ex = _exact(q) or i8
     if i8:
         fused = dict(fused, colsum=pack[4], b_off=pack[5], row_zp=q.zp)
+        if conv_geom is not None:
+            fused["conv"] = tuple(conv_geom) + (pack[6],)
     return ops.gemm(a_op, operand, n_pad, scale=scale, bias=bias, temb=temb, rows_per_batch=rows_per_batch,
                     resid=resid, want_f32=want_f32, k=operand.shape[1],
                     row_scale=q.delta if ex else None, row_period=q.period if ex else 1, **fused)
@@ -115,6 +135,12 @@ def conv(ql, x: Act, *, x2: Optional[Act] = None, upsample: bool = False, gn=Non
     pad = k // 2
     ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
     q = ql.act_qparam(dev)
+    if _implicit_ok(ql, q, h, w, k, s):
+        a_op = ops.act_producer(x.t, src1=None if x2 is None else x2.t, batch=x.b, h=h, w=w, upsample=upsample,
+                                ksize=1, stride=1, gn=gn, act=act, q=q, emit_int=2)
+        out = _gemm(ql, a_op, q, temb=temb, rows_per_batch=ho * wo, resid=resid,
+                    conv_geom=(x.b, h, w, a_op.shape[1]))
+        return Act(out, x.b, ho, wo)
     a_op = ops.act_producer(x.t, src1=None if x2 is None else x2.t, batch=x.b, h=h, w=w, upsample=upsample,
                             ksize=k, stride=s, gn=gn, act=act, q=q, pad_quantized=ql.pad_quantized,
                             emit_int=_emit(ql, q))
@@ -150,11 +176,15 @@ def quant_layer_forward(ql, x: torch.Tensor) -> torch.Tensor:
         k, s = ql.ksize, ql.stride
         if q.mode == ops.Q_KWISE and c % 8:
             raise NotImplementedError("K-wise scales need a channel count that is a multiple of 8")
-        a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=k, stride=s, q=q, pad_quantized=ql.pad_quantized,
-                                emit_int=_emit(ql, q))
         pad = k // 2
         ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
-        y = _gemm(ql, a_op, q, want_f32=True)
+        if _implicit_ok(ql, q, h, w, k, s) and c % 16 == 0:
+            a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=1, stride=1, q=q, emit_int=2)
+            y = _gemm(ql, a_op, q, want_f32=True, conv_geom=(b, h, w, c))
+        else:
+            a_op = ops.act_producer(src, batch=b, h=h, w=w, ksize=k, stride=s, q=q, pad_quantized=ql.pad_quantized,
+                                    emit_int=_emit(ql, q))
+            y = _gemm(ql, a_op, q, want_f32=True)
         return y[:, :n].reshape(b, ho, wo, n).permute(0, 3, 1, 2).contiguous().to(x.dtype)
     shp = x.shape
     x2 = x.detach().reshape(-1, shp[-1])
@@ -265,24 +295,61 @@ def _map_args(attn, dev, sp):
                 qmax=float(wq.level - 1))
 
 
-def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, t: int, s: int) -> torch.Tensor:
-    """q [b*t, C], k/v [b*s, C] -> [b*t, C]: quantise + head split, fused two-pass attention
-    (stand-alone / unfused form: separate dgq_qkv_pack launches)."""
-    dev = q.device
-    heads, d = attn.num_heads, attn.head_dim
+# Score operands in exact form (reference sd.py:171-183 computes q_hat . k_hat in fp32): Q = the bare integers
+# code - zp of aqtizer_q, K = every remaining scale folded in (aqtizer_k's delta in any layout, aqtizer_q's per-channel
+# delta) and split into an fp16 (hi | lo) pair, so the tensor-core product carries ~22 bits and the softmax-map codes
+# follow the reference's down to its own fp32 rounding (tests/test_layerwise_gpu.py reports the residual rate).
+# DGQ_ATTN_SPLIT=0 restores the fp16-rounded operands of round 1 (A/B runs).
+ATTN_SPLIT = os.environ.get("DGQ_ATTN_SPLIT", "1") != "0"
+
+
+def attn_plan(qq: ops.QParam, dp: int) -> dict:
+    """how the Q / K operands of an attention are written under Q quantizer `qq`: q_int (bare integers), q_scale /
+    q_period (scalar / per-token delta of Q, applied by the kernel through alpha), kfold (per-channel delta of Q,
+    folded into K), split (K as an fp16 hi | lo pair)."""
+    plan = dict(q_int=False, q_scale=None, q_period=1, kfold=None, split=False)
+    if not ATTN_SPLIT or qq.mode == ops.Q_NONE or not qq.int_ok:
+        return plan
+    plan.update(q_int=True, split=True)
+    if qq.mode == ops.Q_KWISE:
+        plan["kfold"] = qq.delta
+    else:
+        plan["q_scale"], plan["q_period"] = qq.delta, qq.period
+    return plan
+
+
+def _attn_plan(attn, dev, use_aq: bool, dp: int) -> dict:
+    return attn_plan(_attn_qparam(attn.aqtizer_q, attn, dev) if use_aq else ops.NOQ, dp)
+
+
+def attention_from_projections(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, t: int, s: int, heads: int,
+                               d: int, qq: ops.QParam, qk: ops.QParam, qv: ops.QParam, *, start_peak: bool = False,
+                               **attn_args):
+    """Stand-alone form of the attention path (separate dgq_qkv_pack launches instead of the fused GEMM epilogues):
+    projections q [b*t, heads*d], k / v [b*s, heads*d] under the quantizers qq / qk / qv -> ops.attention(...)."""
     dp = (d + 63) // 64 * 64
+    plan = attn_plan(qq, dp)
+    qo = ops.qkv_pack(q, b, t, heads, d, dp, q=qq, emit_int=plan["q_int"])
+    ko = ops.qkv_pack(k, b, s, heads, d, dp, skip_first=start_peak, q=qk, kfold=plan["kfold"], split=plan["split"])
+    vo = ops.qkv_pack(v, b, s, heads, d, dp, transpose=True, q=qv)
+    return ops.attention(qo, ko, vo, d, start_peak=start_peak, q_scale=plan["q_scale"], q_period=plan["q_period"],
+                         k_split=plan["split"], **attn_args)
+
+
+def attention_core(attn, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, t: int, s: int, *,
+                   want_codes: bool = False, out_dtype=None):
+    """q [b*t, C], k/v [b*s, C] -> [b*t, C]: quantise + head split, fused two-pass attention
+    (stand-alone / unfused form).  want_codes: also the integer codes of the softmax map (verification),
+    returned as (out, codes)."""
+    dev = q.device
     use_aq = bool(getattr(attn, "use_aq", False))
     sp = bool(getattr(attn, "start_peak", False)) and use_aq
-    qq = ops.qkv_pack(q, b, t, heads, d, dp, q=_attn_qparam(attn.aqtizer_q, attn, dev) if use_aq else ops.NOQ)
-    kk = ops.qkv_pack(k, b, s, heads, d, dp, skip_first=sp,
-                      q=_attn_qparam(attn.aqtizer_k, attn, dev) if use_aq else ops.NOQ)
-    vv = ops.qkv_pack(v, b, s, heads, d, dp, transpose=True,
-                      q=_attn_qparam(attn.aqtizer_v, attn, dev) if use_aq else ops.NOQ)
-    if not use_aq:
-        out, _ = ops.attention(qq, kk, vv, d, map_mode=ops.MAP_NONE, out_dtype=ops.ACT_DTYPE)
-        return out
-    out, _ = ops.attention(qq, kk, vv, d, out_dtype=ops.ACT_DTYPE, **_map_args(attn, dev, sp))
-    return out
+    qs = [(_attn_qparam(getattr(attn, n), attn, dev) if use_aq else ops.NOQ) for n in ("aqtizer_q", "aqtizer_k", "aqtizer_v")]
+    margs = _map_args(attn, dev, sp) if use_aq else dict(map_mode=ops.MAP_NONE)
+    margs.pop("start_peak", None)
+    res = attention_from_projections(q, k, v, b, t, s, attn.num_heads, attn.head_dim, *qs, start_peak=sp,
+                                     out_dtype=out_dtype or ops.ACT_DTYPE, want_codes=want_codes, **margs)
+    return (res[0], res[2]) if want_codes else res[0]
 
 
 OVERLAP = True  # independent launches on forked streams: Q/K/V projections of one attention side by side
@@ -329,12 +396,17 @@ class _Fork:
             t.record_stream(torch.cuda.current_stream())
 
 
-def _qkv_gemm(attn, which: int, x, qin, q2, b, tok, dst, sp):
+def _qkv_gemm(attn, which: int, x, qin, q2, b, tok, dst, sp, plan):
     heads, d = attn.num_heads, attn.head_dim
     dp = (d + 63) // 64 * 64
     ql = (attn.to_q, attn.to_k, attn.to_v)[which]
+    extra = {}
+    if which == 0:
+        extra = dict(q2_emit_int=int(plan["q_int"]))
+    elif which == 1:
+        extra = dict(kfold=plan["kfold"], k_split=plan["split"])
     _gemm(ql, x, qin, epi=ops.EPI_QKV, q2=q2, out=dst,
-          qkv=(heads, d, dp, tok, (tok + 7) // 8 * 8, which == 2, sp and which == 1))
+          qkv=(heads, d, dp, tok, (tok + 7) // 8 * 8, which == 2, sp and which == 1), **extra)
 
 
 def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torch.Tensor], kv=None) -> torch.Tensor:
@@ -354,13 +426,14 @@ def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torc
     sp = bool(getattr(attn, "start_peak", False)) and use_aq
     aq = [(_attn_qparam(getattr(attn, n), attn, dev) if use_aq else ops.NOQ) for n in ("aqtizer_q", "aqtizer_k", "aqtizer_v")]
     main = torch.cuda.current_stream()
+    plan = _attn_plan(attn, dev, use_aq, dp)
     dq = ops.qkv_dest(b, t, heads, d, dp, False, dev)
     if kv is not None:
         dk, dv, ev = kv
-        _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
+        _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp, plan)
         main.wait_event(ev)
     else:
-        dk = ops.qkv_dest(b, s, heads, d, dp, False, dev)
+        dk = ops.qkv_dest(b, s, heads, d, dp, False, dev, split=plan["split"])
         dv = ops.qkv_dest(b, s, heads, d, dp, True, dev)
         if OVERLAP and OVERLAP_MASK & 1:
             s1, s2 = _side_streams(dev, 2)
@@ -369,19 +442,20 @@ def attention(attn, xq, xk, xv, qs, b: int, t: int, s: int, resid: Optional[torc
             for st, which, x, dst in ((s1, 1, xk, dk), (s2, 2, xv, dv)):
                 st.wait_event(fork)
                 with torch.cuda.stream(st):
-                    _qkv_gemm(attn, which, x, qs[which], aq[which], b, s, dst, sp)
-            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
+                    _qkv_gemm(attn, which, x, qs[which], aq[which], b, s, dst, sp, plan)
+            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp, plan)
             for st in (s1, s2):
                 ev = torch.cuda.Event()
                 ev.record(st)
                 main.wait_event(ev)
         else:
-            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp)
-            _qkv_gemm(attn, 1, xk, qs[1], aq[1], b, s, dk, sp)
-            _qkv_gemm(attn, 2, xv, qs[2], aq[2], b, s, dv, sp)
+            _qkv_gemm(attn, 0, xq, qs[0], aq[0], b, t, dq, sp, plan)
+            _qkv_gemm(attn, 1, xk, qs[1], aq[1], b, s, dk, sp, plan)
+            _qkv_gemm(attn, 2, xv, qs[2], aq[2], b, s, dv, sp, plan)
     qo = attn.to_out[0].act_qparam(dev)
     margs = _map_args(attn, dev, sp) if use_aq else dict(map_mode=ops.MAP_NONE)
-    o, _ = ops.attention(dq, dk, dv, d, out_q=qo, out_emit_int=_emit(attn.to_out[0], qo), **margs)
+    o, _ = ops.attention(dq, dk, dv, d, out_q=qo, out_emit_int=_emit(attn.to_out[0], qo), q_scale=plan["q_scale"],
+                         q_period=plan["q_period"], k_split=plan["split"], **margs)
     return linear(attn.to_out[0], o, qo, resid=resid)
 
 
@@ -406,25 +480,27 @@ def cross_kv_prefetch(unet, ctx: torch.Tensor) -> dict:
     main = torch.cuda.current_stream()
     cx, cb, s = _ctx_operand(ctx)
     side = _side_streams(dev, 3)[2]
-    dests = []
+    dests, plans = [], []
     for blk in blocks:
         a2 = blk.attn2
         heads, d = a2.num_heads, a2.head_dim
         dp = (d + 63) // 64 * 64
-        dests.append((ops.qkv_dest(cb, s, heads, d, dp, False, dev), ops.qkv_dest(cb, s, heads, d, dp, True, dev)))
+        plans.append(_attn_plan(a2, dev, bool(getattr(a2, "use_aq", False)), dp))
+        dests.append((ops.qkv_dest(cb, s, heads, d, dp, False, dev, split=plans[-1]["split"]),
+                      ops.qkv_dest(cb, s, heads, d, dp, True, dev)))
     fork = torch.cuda.Event()
     fork.record(main)
     side.wait_event(fork)
     with torch.cuda.stream(side):
-        for blk, (dk, dv) in zip(blocks, dests):
+        for blk, (dk, dv), plan in zip(blocks, dests, plans):
             a2 = blk.attn2
             use_aq = bool(getattr(a2, "use_aq", False))
             sp = bool(getattr(a2, "start_peak", False)) and use_aq
             qs = [None, a2.to_k.act_qparam(dev), a2.to_v.act_qparam(dev)]
             aq = [None] + [(_attn_qparam(getattr(a2, n), a2, dev) if use_aq else ops.NOQ) for n in ("aqtizer_k", "aqtizer_v")]
             xkv = ops.row_quant(cx, qs[1:], emit_int=[_emit(a2.to_k, qs[1]), _emit(a2.to_v, qs[2])])
-            _qkv_gemm(a2, 1, xkv[0], qs[1], aq[1], cb, s, dk, sp)
-            _qkv_gemm(a2, 2, xkv[1], qs[2], aq[2], cb, s, dv, sp)
+            _qkv_gemm(a2, 1, xkv[0], qs[1], aq[1], cb, s, dk, sp, plan)
+            _qkv_gemm(a2, 2, xkv[1], qs[2], aq[2], cb, s, dv, sp, plan)
             ev = torch.cuda.Event()
             ev.record(side)
             out[id(a2)] = (dk, dv, ev)

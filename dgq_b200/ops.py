@@ -261,7 +261,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
          row_scale: Optional[torch.Tensor] = None, row_period: int = 1, epi: int = L.EPI_PLAIN,
          q2: QParam = NOQ, q2_emit_int: int = 0, qkv: Optional[tuple] = None,
          colsum: Optional[torch.Tensor] = None, b_off: Optional[torch.Tensor] = None,
-         row_zp: Optional[torch.Tensor] = None):
+         row_zp: Optional[torch.Tensor] = None, kfold: Optional[torch.Tensor] = None, k_split: bool = False,
+         conv: Optional[tuple] = None):
     """a fp16 [m, lda], b fp16 [n_pad, ldb] -> [m, n] (n multiple of 8), fp32 if want_f32 (or `out`
     is fp32) else fp16.  temb / resid must share one dtype (fp16 or fp32).
     epi = EPI_GEGLU: b rows interleaved (pack_weight geglu=True); returns the fp16 operand [m, n/2] of
@@ -269,10 +270,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
     (heads, d, dp, tokens, tp, transpose, skip_first)."""
     m = a.shape[0]
     k = k or min(a.shape[1], b.shape[1])
+    cb = ch = cw = cc = cld = 0
+    csoob = None
+    if conv is not None:                  # implicit 3x3 conv: `a` is the NHWC u8 code tensor [m = b*h*w, c]
+        cb, ch, cw, cc, csoob = conv
+        k, cld = 9 * cc, csoob.shape[1]
     i8 = a.dtype == torch.uint8           # u8 activation codes x s8 weight codes: dgq_gemm_i8
     if i8 and (b.dtype != torch.int8 or colsum is None or row_zp is None or row_scale is None):
         raise TypeError("gemm: a u8 A operand needs the s8 weight operand with its colsum / row_zp / row_scale")
     e2 = _emit_modes([q2], q2_emit_int)[0] if q2.mode != Q_NONE else 0
+    if epi == L.EPI_QKV and q2.mode != Q_NONE:   # Q operand of the attention kernel: bare integers in EVERY scale layout
+        e2 = int(bool(q2_emit_int))
     if epi == L.EPI_GEGLU:
         out = torch.empty(m, n // 2, dtype=torch.uint8 if e2 == 2 else torch.float16, device=a.device)
     elif epi == L.EPI_QKV:
@@ -293,11 +301,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, n: int, *, scale=None, bias=None, tem
                 temb.stride(0) if temb is not None else 0, _p(resid), resid.stride(0) if resid is not None else 0,
                 None if o32 else _p(out), ldc, _p(out) if o32 else None, ep32,
                 epi, q2.struct(e2), heads, d, dp, tokens, tp, int(transpose), int(skip_first),
-                _p(colsum), _p(b_off), _p(row_zp))
+                _p(kfold), int(k_split), _p(colsum), _p(b_off), _p(row_zp), cb, ch, cw, cc, _p(csoob), cld)
     if i8:
         L.check(L.lib().dgq_gemm_i8(C.byref(g), _stream()), "dgq_gemm_i8")
     else:
         L.check(L.lib().dgq_gemm_f16(C.byref(g), _stream()), "dgq_gemm_f16")
+    _count()
+    return out
+
+
+def conv_oob_colsum(operand: torch.Tensor, c: int) -> torch.Tensor:
+    """s8 conv operand [n_pad, 9*c] (tap-major) -> int32 [9, n_pad]: per border class, the column sums of the taps
+    that fall outside the image (dgq_gemm_i8's implicit-conv zero-padding correction)."""
+    n_pad = operand.shape[0]
+    out = torch.empty(9, n_pad, dtype=torch.int32, device=operand.device)
+    L.check(L.lib().dgq_conv_oob_colsum(_p(operand), n_pad, c, _p(out), _stream()), "dgq_conv_oob_colsum")
     _count()
     return out
 
@@ -317,21 +335,26 @@ def weight_to_i8(codes: torch.Tensor, zp: torch.Tensor, n: int, qmax: float):
     return operand, colsum, b_off
 
 
-def qkv_dest(b: int, t: int, heads: int, d: int, dp: int, transpose: bool, device) -> torch.Tensor:
-    """destination of an EPI_QKV GEMM (zero-filled only when it has padding the kernel does not write)"""
+def qkv_dest(b: int, t: int, heads: int, d: int, dp: int, transpose: bool, device, split: bool = False) -> torch.Tensor:
+    """destination of an EPI_QKV GEMM (zero-filled only when it has padding the kernel does not write);
+    split: the K operand as an fp16 (hi | lo) pair, [b, heads, t, 2 dp]"""
     tp = (t + 7) // 8 * 8
-    shape = (b, heads, dp, tp) if transpose else (b, heads, t, dp)
+    shape = (b, heads, dp, tp) if transpose else (b, heads, t, 2 * dp if split else dp)
     padded = dp != d or (transpose and tp != t)
     return (torch.zeros if padded else torch.empty)(shape, dtype=torch.float16, device=device)
 
 
 def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, transpose: bool = False,
-             skip_first: bool = False, q: QParam = NOQ) -> torch.Tensor:
+             skip_first: bool = False, q: QParam = NOQ, emit_int: bool = False, kfold: Optional[torch.Tensor] = None,
+             split: bool = False) -> torch.Tensor:
+    """emit_int: bare integers code - zp (the Q operand); kfold / split: the K operand, value * kfold[channel] as an
+    fp16 (hi | lo) pair [b, heads, t, 2 dp]"""
     tp = (t + 7) // 8 * 8
-    shape = (b, heads, dp, tp) if transpose else (b, heads, t, dp)
+    shape = (b, heads, dp, tp) if transpose else (b, heads, t, 2 * dp if split else dp)
     out = torch.empty(shape, dtype=torch.float16, device=x.device)
     L.check(L.lib().dgq_qkv_pack(_p(x), _is32(x), x.stride(-2), b, t, heads, d, dp, tp, int(transpose),
-                                 int(skip_first), q.struct(), _p(out), _stream()), "dgq_qkv_pack")
+                                 int(skip_first), q.struct(int(bool(emit_int)) if q.mode != Q_NONE else 0), _p(kfold),
+                                 int(split), _p(out), _stream()), "dgq_qkv_pack")
     _count()
     return out
 
@@ -339,8 +362,10 @@ def qkv_pack(x: torch.Tensor, b: int, t: int, heads: int, d: int, dp: int, *, tr
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map_mode: int, real_time: bool = False,
               start_peak: bool = False, delta: Optional[torch.Tensor] = None, qmax: float = 255.0,
               out: Optional[torch.Tensor] = None, want_codes: bool = False, out_dtype=torch.float16,
-              out_q: Optional[QParam] = None, out_emit_int: int = 0):
-    """q [b,h,t,dp], k [b,h,s,dp], vt [b,h,dp,sp] fp16 -> fp16 [b*t, h*d]; returns (out, rt_delta[, codes])."""
+              out_q: Optional[QParam] = None, out_emit_int: int = 0, q_scale: Optional[torch.Tensor] = None,
+              q_period: int = 1, k_split: bool = False):
+    """q [b,h,t,dp], k [b,h,s,dp] (k_split: [b,h,s,2dp] hi | lo), vt [b,h,dp,sp] fp16 -> [b*t, h*d];
+    q_scale[token % q_period]: delta of an integer Q operand.  Returns (out, rt_delta[, codes])."""
     b, heads, t, dp = q.shape
     s, sp = k.shape[2], vt.shape[3]
     dev = q.device
@@ -356,7 +381,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, d: int, *, map
     codes = torch.zeros(b, heads, t, s, dtype=torch.uint8, device=dev) if want_codes else None
     a = L.AttnT(_p(q), _p(k), _p(vt), b, heads, t, s, sp, d, dp, float(d) ** -0.5, map_mode, int(real_time),
                 int(start_peak), _p(delta), qmax, _p(row_max), _p(row_sum), _p(gmax), _p(out), out.stride(0),
-                int(out.dtype == torch.float32), _p(codes), (out_q or NOQ).struct(oe))
+                int(out.dtype == torch.float32), _p(codes), (out_q or NOQ).struct(oe), _p(q_scale), int(q_period),
+                int(k_split))
     L.check(L.lib().dgq_attention(C.byref(a), _stream()), "dgq_attention")
     _count(2)
     return (out, gmax[:1], codes) if want_codes else (out, gmax[:1])

@@ -287,7 +287,8 @@ class QuantLayer(nn.Module):
     def packed(self, geglu: bool = False, i8: bool = False):
         """(operand fp16 [n_pad, K], scale fp32 [n_pad] | None, bias fp32 [n_pad] | None, n_pad).
         geglu: rows interleaved for the fused GEGLU epilogue (cached separately).
-        i8: the s8 operand of dgq_gemm_i8 instead, + (colsum int32 [n_pad], b_off int32 [n_pad] | None)."""
+        i8: the s8 operand of dgq_gemm_i8 instead, + (colsum int32 [n_pad], b_off int32 [n_pad] | None,
+        csoob int32 [9, n_pad] | None: border-class tables of the implicit 3x3 conv)."""
         if i8:
             return self._packed_i8(geglu)
         if self._frozen is not None:
@@ -360,6 +361,8 @@ class QuantLayer(nn.Module):
         _, codes, _ = ops.pack_weight(w.detach().to(torch.float32), wq.delta, wq.zero_point, alpha, qmax, True,
                                       n_pad=n_pad, want_codes=True)
         operand, colsum, b_off = ops.weight_to_i8(codes, wq.zero_point, n, qmax)
+        # implicit-conv border tables (3x3 only; GEGLU never applies to a conv)
+        csoob = ops.conv_oob_colsum(operand, w.shape[1]) if (self.is_conv and self.ksize == 3) else None
         scale = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         scale[:n] = wq.delta.detach().reshape(-1).to(dev, torch.float32)
         bias = None
@@ -376,7 +379,7 @@ class QuantLayer(nn.Module):
             b_off = None if b_off is None else b_off[perm].contiguous()
         if not self._pack:
             self._pack = {}
-        self._pack[("i8", geglu)] = (key, (operand, scale, bias, n_pad, colsum, b_off))
+        self._pack[("i8", geglu)] = (key, (operand, scale, bias, n_pad, colsum, b_off, csoob))
         return self._pack[("i8", geglu)][1]
 
     def _frozen_pack(self, geglu: bool):

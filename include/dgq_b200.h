@@ -182,6 +182,16 @@ typedef struct {
   const int32_t* b_off;  /* [n] e_n = (offset subtracted from the weight codes) - (weight zero point),
                             or NULL when the zero point itself was subtracted (W4: codes - zp fit s8)  */
   const float* row_zp;   /* activation zero point, indexed like row_scale: row_zp[m % row_period]     */
+  /* ---- dgq_gemm_i8, DGQ_EPI_PLAIN: implicit 3x3 / stride 1 / pad 1 convolution (conv_h > 0).  `a` is then the
+   *      NHWC u8 code tensor [conv_b, conv_h, conv_w, conv_c] itself (what a 1x1 producer writes; lda unused),
+   *      m = conv_b * conv_h * conv_w, k = 9 * conv_c with B in tap-major K order (dgq_pack_weight), scalar
+   *      activation scale (row_period = 1).  Replaces F.conv2d(x_hat, w_hat, padding=1) of the per-tensor path
+   *      (quant/quant_layer.py:659): padding taps are EXACT zeros there, i.e. code = zero point, which the
+   *      epilogue restores per border class from conv_csoob[class][n] (dgq_conv_oob_colsum), class =
+   *      3 * (0 top | 1 | 2 bottom) + (0 left | 1 | 2 right).                                               */
+  int conv_b, conv_h, conv_w, conv_c;
+  const int32_t* conv_csoob; /* [9][conv_ldoob] */
+  int conv_ldoob;
 } dgq_gemm_t;
 #define DGQ_EPI_PLAIN 0
 #define DGQ_EPI_GEGLU 1
@@ -205,6 +215,10 @@ int dgq_gemm_i8(const dgq_gemm_t* host_args, void* stream);
  *   (b_off[n] = 128 - zp[n]); colsum[n] = sum_k operand[n, k]; rows >= n are zero.                           */
 int dgq_weight_to_i8(const uint8_t* codes, const float* zp, int n, int n_pad, int k_out, float qmax,
                      int8_t* operand, int32_t* colsum, int32_t* b_off, void* stream);
+/* border-class tables of the implicit 3x3 convolution: operand s8 [n_pad, 9 * c] (tap-major) ->
+ * csoob[cls][n] = sum over the taps that lie outside the image for border class cls of sum_c operand[n, tap*c + ch]
+ * (cls 4, the interior, is all zero).  csoob: int32 [9][n_pad].                                               */
+int dgq_conv_oob_colsum(const int8_t* operand, int n_pad, int c, int32_t* csoob, void* stream);
 
 /* ---- attention with quantised operands and quantised softmax map
  *      (Attention.Attention_forward, diffusers_rewrite/sd.py:151-207; T2ILogQuantizer) ---------
@@ -245,7 +259,7 @@ typedef struct {
                            mode NONE: O is stored as is; emit_int = 2: u8 codes (ldo in bytes) */
   /* score operands in exact form (sd.py:171-183: q_hat . k_hat): q holds the bare integers code - zp of aqtizer_q
    * and q_scale[token % q_scale_period] its scalar / per-token delta (NULL: none, or folded into k); k_split = 1:
-   * k is [b, heads, s, 2 dp] = fp16 (hi | lo) of the fully scaled key (dgq_gemm_t.k_split), dp <= 128.          */
+   * k is [b, heads, s, 2 dp] = fp16 (hi | lo) of the fully scaled key (dgq_gemm_t.k_split).                     */
   const float* q_scale;
   int q_scale_period;
   int k_split;

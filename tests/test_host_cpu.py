@@ -168,7 +168,7 @@ def _gloo_worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     # every rank owns a contiguous slice of the prompt batch, seeded by global position
-    host = bench.make_inputs(torch, 2, seed=1000 + rank)
+    host = bench.make_inputs(torch, bench.CONFIGS[4], 2, seed=1000 + rank)
     y = host[0][:, :, :2, :2].contiguous()            # stand-in for this rank's predicted latents
     gather = [torch.empty_like(y) for _ in range(world)]
     dist.all_gather(gather, y)
@@ -188,9 +188,22 @@ def test_sharded_gather_world2_gloo(tmp_path):
     r = torch.load(out)
     assert r["ms"].item() == 2.0
     for rank in range(2):
-        want = bench.make_inputs(torch, 2, seed=1000 + rank)[0][:, :, :2, :2]
+        want = bench.make_inputs(torch, bench.CONFIGS[4], 2, seed=1000 + rank)[0][:, :, :2, :2]
         assert torch.equal(r["g"][rank], want)
     assert not torch.equal(r["g"][0], r["g"][1])
+
+
+def test_strong_scaling_shard_plan():
+    """config 5 (src/gen4eval_SDXL.py:116): a fixed prompt batch split contiguously over the ranks, micro-batches <= 16;
+    every prompt is run exactly once whatever the GPU count."""
+    import bench
+    for total in (8, 16, 64, 512, 100):
+        for world in (1, 2, 4, 8):
+            shares = [sum(bench.shard_plan(total, world, r, 16)) for r in range(world)]
+            assert sum(shares) == total and max(shares) - min(shares) <= 1
+            assert all(mb <= 16 for r in range(world) for mb in bench.shard_plan(total, world, r, 16))
+    assert bench.shard_plan(512, 8, 3, 16) == [16, 16, 16, 16]
+    assert [bench.shard_plan(4, 8, r, 16) for r in range(8)].count([1]) == 4
 
 
 def test_compiled_header_rejects_foreign_files(tmp_path):

@@ -151,3 +151,40 @@ def test_producers_emit_u8_codes(mode):
         else:        # exact-zero padding: the verification output marks those taps 0, the operand holds the code zp
             fi = ops.act_producer(src, batch=b, h=h, w=h, ksize=3, stride=stride, q=qp, pad_quantized=False, emit_int=1)
             assert torch.equal(u8.float(), fi.float() + qp.zp[0])
+
+
+@pytest.mark.parametrize("bsz,ci,co,hw", [(1, 64, 96, 8), (2, 64, 96, 8), (3, 64, 40, 8), (2, 320, 320, 16), (1, 128, 64, 32),
+                                          (2, 192, 640, 64), (1, 320, 320, 64)])
+@pytest.mark.parametrize("wbits,abits", [(8, 8), (8, 6), (4, 8)])
+def test_implicit_conv_matches_im2col_and_oracle(bsz, ci, co, hw, wbits, abits):
+    """3x3 / stride 1 / pad 1 conv with a per-tensor activation scale (reference quant_layer.py:659: F.conv2d on
+    x_hat with EXACT-zero padding): the implicit GEMM (NHWC codes gathered by 4-D TMA, border-class zero-point
+    correction) == the im2col producer + GEMM == the oracle.  Patch shapes 8x8x2 / 16x8 are all exercised."""
+    from dgq_b200 import engine, ops
+    from oracle import dgq_oracle as O
+    g = torch.Generator().manual_seed(bsz + ci + hw + wbits)
+    torch.manual_seed(5)
+    layer = nn.Conv2d(ci, co, 3, 1, 1)
+    x = torch.randn(bsz, ci, hw, hw, generator=g) * 1.5
+    d, z = _scales(g, 1, 2 ** abits)
+    w_cpu, b_cpu = layer.weight.detach().clone(), layer.bias.detach().clone()
+    ql = _layer(layer, wbits, abits, d[0], z[0], False)
+    q = ql.act_qparam(torch.device(DEV))
+    assert engine._implicit_ok(ql, q, hw, hw, 3, 1)
+    try:
+        engine.IMPLICIT_CONV = True
+        n0 = ops.LAUNCHES
+        y_imp = ql(x.to(DEV))
+        n_imp = ops.LAUNCHES - n0
+        engine.IMPLICIT_CONV = False
+        y_col = ql(x.to(DEV))
+    finally:
+        engine.IMPLICIT_CONV = True
+    assert n_imp == 2           # one NHWC quantize launch + one GEMM
+    wd, wz = O.channel_minmax_scale(w_cpu, 2 ** wbits)
+    sd = {"l.w": w_cpu, "l.b": b_cpu, "l.wqtizer.delta": wd, "l.wqtizer.zero_point": wz}
+    ref = O.quant_layer(x, sd, {"l.aqtizer.delta": d[0], "l.aqtizer.zero_point": z[0]}, "l",
+                        O.QConfig(wbits=wbits, abits=abits), padding=1)
+    scale = ref.abs().max()
+    assert ((y_imp.cpu() - y_col.cpu()).abs().max() / scale).item() < 1e-6
+    assert ((y_imp.cpu() - ref).abs().max() / scale).item() < 2e-5
