@@ -126,6 +126,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <int MODE, bool CODES>
 __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2)[16], float alpha, float gamma,
                                           float qcap, float qmax, int col0, int s_len, uint8_t* code_row) {
+  // qcap is a POWER OF TWO (64, see the caller): s * (-alpha / qcap) + gamma / qcap is then the same rounding as
+  // gamma - s * alpha with the exponent shifted, and y * qcap is exact -- the code below IS rint(gamma - s * alpha).
+  // (Round 1 used qcap = 126: two roundings, ~7e-6 of a code step, i.e. code flips at ~1.5e-5 that the verification
+  // output -- computed by the direct formula -- did not even show.)
   const float q_inv = __frcp_rn(qcap);
   const float a_sat = -alpha * q_inv, g_sat = gamma * q_inv;   // loop-invariant: hoisted by the compiler
 #pragma unroll
@@ -134,25 +138,34 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const float sc = __uint_as_float(r[i + e]);
-      float val;
+      float val, cd = 0.f;
       if (MODE == DGQ_MAP_LOG2) {
-        // x / qcap = gamma / qcap - s * alpha / qcap, clamped to [0, 1] by the FMA's own .sat (the two FMNMX of
-        // an explicit clamp run on the half-rate ALU pipe, which bounded this loop); rint(x) through the
-        // 1.5 * 2^23 magic add of a second FMA; 2^-code rebuilt from the exponent field by one IMAD
-        float y;
-        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(sc), "f"(a_sat), "f"(g_sat));
-        const uint32_t yb = __float_as_uint(fmaf(y, qcap, 12582912.0f));
-        val = __uint_as_float(yb * 0xFF800000u + 0x3F800000u);
+        if (qmax >= qcap) {
+          // x / qcap clamped to [0, 1] by the FMA's own .sat (the two FMNMX of an explicit clamp run on the
+          // half-rate ALU pipe, which bounded this loop); rint(x) through the 1.5 * 2^23 magic add of a second FMA;
+          // 2^-code rebuilt from the exponent field by one IMAD.  Codes beyond qcap (>= 25 already flush to 0 in the
+          // fp16 operand) stay at qcap: 2^-64.
+          float y;
+          asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(sc), "f"(a_sat), "f"(g_sat));
+          const uint32_t yb = __float_as_uint(fmaf(y, qcap, 12582912.0f));
+          val = __uint_as_float(yb * 0xFF800000u + 0x3F800000u);
+          if (CODES) {
+            cd = static_cast<float>(yb - 0x4B400000u);      // the code the operand was built from ...
+            if (cd >= qcap) cd = fminf(rintf(fmaxf(fmaf(-alpha, sc, gamma), 0.f)), qmax);   // ... or beyond the cap
+          }
+        } else {
+          // fewer levels than the cap (softmax_a_bit <= 4): explicit clamp at qmax
+          cd = fminf(rintf(fmaxf(fmaf(-alpha, sc, gamma), 0.f)), qmax);
+          val = __uint_as_float(0x3F800000u - (static_cast<uint32_t>(cd) << 23));
+        }
       } else if (MODE == DGQ_MAP_UNIFORM) {
         val = fminf(rintf(ex2_approx(fmaf(alpha, sc, -gamma))), qmax);
+        cd = val;
       } else {
         val = (col0 + i + e < s_len) ? ex2_approx(fmaf(alpha, sc, -gamma)) : 0.f;
       }
       if (CODES) {
-        if (col0 + i + e < s_len && MODE != DGQ_MAP_NONE) {
-          const float cd = MODE == DGQ_MAP_LOG2 ? fminf(rintf(fmaxf(fmaf(-alpha, sc, gamma), 0.f)), qmax) : val;
-          code_row[col0 + i + e] = static_cast<uint8_t>(cd);
-        }
+        if (col0 + i + e < s_len && MODE != DGQ_MAP_NONE) code_row[col0 + i + e] = static_cast<uint8_t>(cd);
       }
       pv[e] = val;
     }
@@ -487,7 +500,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float delta = 1.0f;
         if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
         const float lg_delta = MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f;
-        const float qcap = fminf(p.qmax, 126.f);
+        const float qcap = 64.f;                  // power of two: see map_chunk
         const float beta = rok ? (p.row_max[rix] + log2f(p.row_sum[rix])) : 0.f;
         const float gamma = beta + lg_delta;
         float p0 = 0.f;                           // un-quantised start-peak probability of this row
@@ -630,7 +643,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float delta = 1.0f;
         if (MODE != DGQ_MAP_NONE) delta = p.real_time ? p.gmax[0] : __ldg(p.delta);
         const float lg_delta = MODE != DGQ_MAP_NONE ? log2f(delta) : 0.f;
-        const float qcap = fminf(p.qmax, 126.f);
+        const float qcap = 64.f;                  // power of two: see map_chunk
         float beta[2], p0[2] = {0.f, 0.f};        // p0: un-quantised start-peak probability of this row
 #pragma unroll
         for (int h = 0; h < 2; ++h) beta[h] = row_ok[h] ? (p.row_max[ridx[h]] + log2f(p.row_sum[ridx[h]])) : 0.f;

@@ -641,7 +641,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       auto plain = [&](auto full_tag) {
         constexpr bool kFullTile = decltype(full_tag)::value;   // interior tile: no row / column bounds
-        float4 t_cur[8], t_nxt[8];
+        float4 t_cur[8];
         auto ldres = [&](int c, float4 (&t)[8]) {
           const int n = ncol0 + c * 32 + cq;
 #pragma unroll
@@ -662,7 +662,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             t[rr] = u;
           }
         };
-        if (has_resid && c_begin < c_end) ldres(c_begin, t_cur);
         epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -670,7 +669,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (c_begin < c_end) tmem_ld_32x32(t_row + c_begin * 32, r);
         for (int c = c_begin; c < c_end; ++c) {
           const int j0 = c * 32;
-          if (has_resid && c + 1 < c_end) ldres(c + 1, t_nxt);
+          // the chunk's residual segments are requested before the accumulator wait: their latency is covered by
+          // phase A and by the other epilogue warps (a second, one-chunk-ahead buffer costs 32 registers and spilled)
+          if (has_resid) ldres(c, t_cur);
           tc_wait_ld();
 #pragma unroll
           for (int v = 0; v < 8; ++v)
@@ -742,10 +743,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
           __syncwarp();
-          if (has_resid) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
-          }
         }
       };
       // interior tiles with no per-row time-embedding rows take the branch-free instantiation

@@ -142,6 +142,77 @@ __global__ void __launch_bounds__(512, 1) ldtm_kernel(int iters, unsigned long l
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// tcgen05.ld while the tensor core is accumulating into the OTHER half of tensor memory: warp 0 = MMA issuer
+// (kind::f16 or kind::i8, M = 128, N = 256, columns 0..255), warps 1.. read columns 256..511 in a loop -- what a
+// double-buffered GEMM epilogue does.  Reports both rates.
+template <int KIND>
+__global__ void __launch_bounds__(544, 1) ldtm_mma_kernel(int mma_iters, int ld_iters, unsigned long long* cyc, uint32_t* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_a = smem;
+  uint8_t* s_b = smem + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  uint32_t acc = 0;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = KIND == 0 ? umma_idesc_f16(128, 256) : umma_idesc_i8(128, 256, false, true);
+      const uint64_t da = umma_desc_sw128(smem_u32(s_a)), db = umma_desc_sw128(smem_u32(s_b));
+      const unsigned long long t0 = clock64();
+      for (int it = 0; it < mma_iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (KIND == 0) tc_mma_f16(tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+          else tc_mma_i8(tmem, da + 2 * ks, db + 2 * ks, idesc, 1u);
+        }
+      }
+      tc_commit(&bar[0]);
+      mbar_wait(&bar[0], 0);
+      if (blockIdx.x == 0) cyc[0] = clock64() - t0;
+    }
+  } else {
+    const int w = warp - 1;
+    const uint32_t base = tmem + (static_cast<uint32_t>((w & 3) * 32) << 16) + 256 + ((w >> 2) * 64) % 256;
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < ld_iters; ++it) {
+      uint32_t r[32];
+      tmem_ld_32x32(base + (it & 1) * 32, r);
+      tc_wait_ld();
+      acc ^= r[0] ^ r[13] ^ r[31];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 32) cyc[1] = clock64() - t0;
+  }
+  if (acc == 0x12345678u) sink[threadIdx.x] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int KIND>
+static void run_ldtm_mma(int ld_warps, unsigned long long* d_cyc, uint32_t* d_sink) {
+  const int smem = 16384 + 32768 + 1024 + 64;
+  CK(cudaFuncSetAttribute(ldtm_mma_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int mma_iters = 20000, ld_iters = 20000;
+  unsigned long long cyc[2] = {0, 0};
+  for (int rep = 0; rep < 2; ++rep) {
+    ldtm_mma_kernel<KIND><<<148, 32 + ld_warps * 32, smem>>>(mma_iters, ld_iters, d_cyc, d_sink);
+    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaMemcpy(cyc, d_cyc, 16, cudaMemcpyDeviceToHost));
+  printf("ldtm under kind::%s MMA, %2d reader warps: tcgen05.ld %6.1f B/clk per SM (alone: see above), MMA %6.1f cycles per instruction\n",
+         KIND == 0 ? "f16" : "i8 ", ld_warps, static_cast<double>(ld_warps) * ld_iters * 4096.0 / cyc[1],
+         static_cast<double>(cyc[0]) / (mma_iters * 4.0));
+}
+
 template <int DEPTH>
 static void run_ldtm(int warps, int iters, unsigned long long* d_cyc, uint32_t* d_sink) {
   unsigned long long cyc = 0;
@@ -171,6 +242,10 @@ int main() {
   for (int warps : {4, 8, 16}) {
     run_ldtm<1>(warps, 20000, d_cyc, d_sink);
     run_ldtm<2>(warps, 20000, d_cyc, d_sink);
+  }
+  for (int warps : {8, 16}) {
+    run_ldtm_mma<0>(warps, d_cyc, d_sink);
+    run_ldtm_mma<1>(warps, d_cyc, d_sink);
   }
   return 0;
 }
