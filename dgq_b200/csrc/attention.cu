@@ -235,43 +235,53 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   //   it = item counter of this CTA;  g = K/V tile counter;  u = g * nh + h = score-tile step counter
   //   S / P' buffer = u & 1;  Q tile number = it * nh + h;  O accumulator number = it * nh + h
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA loader: Q and K
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA loader: Q and K (warp-converged, one
+    // elected lane issues: see the PV issuer)
+    {
       uint32_t g = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int qg = item % q_groups, bh = item / q_groups;
         for (uint32_t h = 0; h < nh; ++h) {
           const uint32_t qn = it * nh + h, qb = qn % nqb;
           mbar_wait(&bars[B_QEMPTY + qb], ((qn / nqb) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[B_QFULL + qb], q_bytes);
-          for (int c = 0; c < dchunks; ++c)
-            tma_load_3d(s_q + qb * q_bytes + c * kChunkBytes, &tm_q, &bars[B_QFULL + qb], c * 64,
-                        (qg * static_cast<int>(nh) + static_cast<int>(h)) * kTileQ, bh);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars[B_QFULL + qb], q_bytes);
+            for (int c = 0; c < dchunks; ++c)
+              tma_load_3d(s_q + qb * q_bytes + c * kChunkBytes, &tm_q, &bars[B_QFULL + qb], c * 64,
+                          (qg * static_cast<int>(nh) + static_cast<int>(h)) * kTileQ, bh);
+          }
+          __syncwarp();
         }
         for (int j = 0; j < p.nkv; ++j) {
           for (int part = 0; part < kparts; ++part, ++g) {     // g counts ring entries here
             const uint32_t slot = g % nkb;
             mbar_wait(&bars[B_KEMPTY + slot], ((g / nkb) & 1) ^ 1);
-            mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
-            for (int c = 0; c < dchunks; ++c)
-              tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], (part * dchunks + c) * 64,
-                          j * kTileK, bh);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars[B_KFULL + slot], q_bytes);
+              for (int c = 0; c < dchunks; ++c)
+                tma_load_3d(s_k + slot * q_bytes + c * kChunkBytes, &tm_k, &bars[B_KFULL + slot], (part * dchunks + c) * 64,
+                            j * kTileK, bh);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (PASS == 2 && warp == 2) {
-    // ------------------------------------------------------------------ V loader (own ring, own thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ V loader (own ring, own warp)
+    {
       uint32_t g = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const int bh = item / q_groups;
         for (int j = 0; j < p.nkv; ++j, ++g) {
           const uint32_t slot = g % nvb;
           mbar_wait(&bars[B_VEMPTY + slot], ((g / nvb) & 1) ^ 1);
-          mbar_arrive_expect_tx(&bars[B_VFULL + slot], v_stage);
-          for (int c = 0; c < 2; ++c)
-            tma_load_3d(s_v + slot * v_stage + c * (p.dp * 128), &tm_v, &bars[B_VFULL + slot], j * kTileK + c * 64, 0, bh);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bars[B_VFULL + slot], v_stage);
+            for (int c = 0; c < 2; ++c)
+              tma_load_3d(s_v + slot * v_stage + c * (p.dp * 128), &tm_v, &bars[B_VFULL + slot], j * kTileK + c * 64, 0, bh);
+          }
+          __syncwarp();
         }
       }
     }
@@ -279,8 +289,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // ------------------------------------------------------------------ PV issuer (own thread: every
     // mbarrier wait / commit costs the issuing thread ~100+ cycles of latency, so one thread issuing
     // both QK^T and PV serialises ~12 such operations per 128 x 128 step and becomes the critical path)
-    if (lane == 0) {
+    // All 32 lanes run the loop in lock-step -- loop counters, barrier addresses and operand descriptors are then
+    // warp-uniform and stay on the uniform datapath -- and ONE elected lane issues the tcgen05 instructions.  (As
+    // `if (lane == 0) { loop }` the descriptors lived in per-thread registers and every MMA dragged a chain of
+    // R2UR moves: ncu showed the QK^T issuer busy 75 % of the kernel and every other role waiting on it.)
+    {
       const uint32_t idesc_o = umma_idesc_f16(kTileQ, p.dp);
+      const uint64_t dp0 = umma_desc_sw128(smem_u32(s_p)), dv0 = umma_desc_sw128(smem_u32(s_v));
+      const uint32_t cstep = kChunkBytes >> 4, vstep = v_stage >> 4, vcstep = static_cast<uint32_t>(p.dp * 128) >> 4;
       // O[on] += P'(u) V(g):  u = score-tile step, g = its K/V tile, on = O accumulator number,
       // first / last = first / last K tile of the item, lastq = last query half using V(g)
       auto issue_pv = [&](uint32_t u, uint32_t g, uint32_t on, bool first, bool last, bool lastq) {
@@ -289,17 +305,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(&bars[B_PFULL + pb], (u >> 1) & 1);
         if (first) mbar_wait(&bars[B_OEMPTY + ob], ((on / nob) & 1) ^ 1);   // the epilogue drained this accumulator
         tc_fence_after();
+        const uint64_t da0 = dp0 + pb * 2 * cstep, db0 = dv0 + slot * vstep;
+        const uint32_t d_o = tmem_o + ob * p.dp;
+        if (elect_one()) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint64_t da = umma_desc_sw128(smem_u32(s_p + pb * 2 * kChunkBytes + c * kChunkBytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(s_v + slot * v_stage + c * (p.dp * 128)));
+          for (int c = 0; c < 2; ++c) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc_mma_f16(tmem_o + ob * p.dp, da + 2 * ks, db + 2 * ks, idesc_o, (!first || (c | ks) != 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_f16(d_o, da0 + c * cstep + 2 * ks, db0 + c * vcstep + 2 * ks, idesc_o, (!first || (c | ks) != 0) ? 1u : 0u);
+          }
+          if (lastq) tc_commit(&bars[B_VEMPTY + slot]);
+          tc_commit(&bars[B_PEMPTY + pb]);
+          if (last) tc_commit(&bars[B_OFULL + ob]);
         }
-        if (lastq) tc_commit(&bars[B_VEMPTY + slot]);
-        tc_commit(&bars[B_PEMPTY + pb]);
-        if (last) tc_commit(&bars[B_OFULL + ob]);
+        __syncwarp();
       };
       uint32_t u = 0, g = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
@@ -310,14 +329,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ QK^T issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ QK^T issuer (warp-converged, one elected
+    // lane issues: see the PV issuer)
+    {
       const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileK);
+      const uint64_t dq0 = umma_desc_sw128(smem_u32(s_q)), dk0 = umma_desc_sw128(smem_u32(s_k));
+      const uint32_t cstep = kChunkBytes >> 4, qstep = q_bytes >> 4;      // descriptor address field: 16-byte units
       uint32_t u = 0, g = 0, it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         for (int j = 0; j < p.nkv; ++j, ++g, u += nh) {
-          // S(u + h) = Q_h . K_hi (+ Q_h . K_lo): the parts arrive as separate ring entries, so the lo part of a tile
-          // can share its buffer with the hi part when shared memory is short (dp = 128 / 192)
+          // S(u + h) = Q_h . K_hi (+ Q_h . K_lo): the parts arrive as separate ring entries
+          if (nkb >= static_cast<uint32_t>(kparts)) {
+            // both parts resident: one query half at a time, so S(u) is committed without waiting for the OTHER
+            // half's S buffer -- the two softmax groups must stay decoupled (a part-outer order locks them in step)
+            for (int part = 0; part < kparts; ++part) {
+              const uint32_t gp = g * kparts + part;
+              mbar_wait(&bars[B_KFULL + gp % nkb], (gp / nkb) & 1);
+            }
+            const uint32_t slot0 = (g * kparts) % nkb, slot1 = (g * kparts + kparts - 1) % nkb;
+            for (uint32_t h = 0; h < nh; ++h) {
+              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu & 1;
+              if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
+              mbar_wait(&bars[B_SEMPTY + sb], ((uu >> 1) & 1) ^ 1);
+              tc_fence_after();
+              const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot0 * qstep, db1 = dk0 + slot1 * qstep;
+              const uint32_t d_s = tmem_base + sb * kTileK;
+              if (elect_one()) {
+                for (int c = 0; c < dchunks; ++c) {
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    tc_mma_f16(d_s, da0 + c * cstep + 2 * ks, db0 + c * cstep + 2 * ks, idesc_s, (c | ks) != 0 ? 1u : 0u);
+                }
+                if (kparts == 2) {
+                  for (int c = 0; c < dchunks; ++c) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      tc_mma_f16(d_s, da0 + c * cstep + 2 * ks, db1 + c * cstep + 2 * ks, idesc_s, 1u);
+                  }
+                }
+                tc_commit(&bars[B_SFULL + sb]);
+                if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);         // last read of this Q tile
+                if (h == nh - 1) {                                           // last read of this K tile
+                  tc_commit(&bars[B_KEMPTY + slot0]);
+                  if (kparts == 2) tc_commit(&bars[B_KEMPTY + slot1]);
+                }
+              }
+              __syncwarp();
+            }
+            continue;
+          }
+          // hi and lo share ONE buffer (dp = 128 / 192 with the split): part by part
           for (int part = 0; part < kparts; ++part) {
             const uint32_t gp = g * kparts + part, slot = gp % nkb;
             mbar_wait(&bars[B_KFULL + slot], (gp / nkb) & 1);
@@ -328,18 +389,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 mbar_wait(&bars[B_SEMPTY + sb], ((uu >> 1) & 1) ^ 1);
               }
               tc_fence_after();
-              for (int c = 0; c < dchunks; ++c) {
-                const uint64_t da = umma_desc_sw128(smem_u32(s_q + qb * q_bytes + c * kChunkBytes));
-                const uint64_t db = umma_desc_sw128(smem_u32(s_k + slot * q_bytes + c * kChunkBytes));
+              const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot * qstep;
+              const uint32_t d_s = tmem_base + sb * kTileK;
+              if (elect_one()) {
+                for (int c = 0; c < dchunks; ++c) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  tc_mma_f16(tmem_base + sb * kTileK, da + 2 * ks, db + 2 * ks, idesc_s, (part | c | ks) != 0 ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks)
+                    tc_mma_f16(d_s, da0 + c * cstep + 2 * ks, db0 + c * cstep + 2 * ks, idesc_s, (part | c | ks) != 0 ? 1u : 0u);
+                }
+                if (part == kparts - 1) {
+                  tc_commit(&bars[B_SFULL + sb]);
+                  if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);       // last read of this Q tile
+                }
+                if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this ring entry
               }
-              if (part == kparts - 1) {
-                tc_commit(&bars[B_SFULL + sb]);
-                if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);       // last read of this Q tile
-              }
-              if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this ring entry
+              __syncwarp();
             }
           }
         }

@@ -189,7 +189,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs of a pair)
-    if (lane == 0) {
+    // All 32 lanes run the loop in lock-step (indices, barrier addresses and coordinates stay warp-uniform, on the
+    // uniform datapath) and one elected lane issues -- as `if (lane == 0) { loop }` every descriptor lived in
+    // per-thread registers and each tcgen05 / TMA instruction dragged a chain of R2UR moves (attention.cu, round 2).
+    {
       uint32_t stage = 0, phase = 0;
       const uint32_t tx = (kABytes + static_cast<uint32_t>(b_rows) * kBK * 2) * kCtas;
       for (int tile = worker; tile < total_tiles; tile += workers) {
@@ -200,6 +203,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (cv) cv_origin(m_blk, px0, py0, b0);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           if (cv) {
             const int tap = kb / p.cv_cblocks, ka = (kb - tap * p.cv_cblocks) * kBKe;
             const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
@@ -221,14 +225,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             tma_load_2d_pair(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBKe, row_a);
             tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBKe, row_b);
           }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only; warp-converged, one
+    // elected lane issues, operand descriptors precomputed on the uniform datapath)
+    if (rank == 0) {
       const uint32_t idesc = kI8 ? umma_idesc_i8(kBM * kCtas, p.bn, false, true) : umma_idesc_f16(kBM * kCtas, p.bn);
+      const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a)), db0 = umma_desc_sw128(smem_u32(smem_b));
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = worker; tile < total_tiles; tile += workers) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -237,8 +245,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kABytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t da = da0 + stage * (kABytes >> 4), db = db0 + stage * (Cfg::kBBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < kBK / 16; ++ks) {
             // advancing 16 halves / 32 bytes along K inside the swizzle atom: +2 in the >>4 address field
@@ -253,9 +261,14 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           // frees the smem stage (in both CTAs) once these MMAs retire
           if (kCtas == 2) tc_commit_pair(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
           if (kI8 && kCtas == 2 && need_rowsum) tc_commit_pair(&mdone_bar[stage]);   // the row-sum warps' cue
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (kCtas == 2) tc_commit_pair(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);  // accumulator complete
+        if (elect_one()) {
+          if (kCtas == 2) tc_commit_pair(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -312,7 +325,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int nch = p.bn / kUnit;
     const int c_begin = (nch * split + kSplit - 1) / kSplit;
     const int c_end = (nch * (split + 1) + kSplit - 1) / kSplit;
-    const size_t esz = p.ep_is_f32 ? 4 : 2;
     const bool temb_tile = p.temb != nullptr && (p.rows_per_batch % (kBM * kCtas)) == 0;
     float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_epi + 2 * kEpiTab * kMaxBN) +
                                           (warp - 2) * EpiCfg<kEpi>::kStgBytes);
@@ -613,6 +625,157 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
+      if constexpr (!kI8) {
+      // ---- kind::f16 plain epilogue (round 1 form): the affine in phase A (thread = row), per-column tables from
+      // shared memory, residual segments prefetched one chunk ahead; fits 168 registers without spilling.
+      const size_t esz = p.ep_is_f32 ? 4 : 2;
+      const char* temb_row = (p.temb != nullptr && !temb_tile && row_ok)
+                                 ? static_cast<const char*>(p.temb) + static_cast<size_t>(row / p.rows_per_batch) * p.ld_temb * esz
+                                 : nullptr;
+      float4 t_cur[8], t_nxt[8];
+      auto load_resid = [&](int c, float4 (&t)[8]) {
+        const int n = ncol0 + c * 32 + cq;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const int grow = warp_row0 + rr * 4 + rl0;
+          float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (grow < p.m && n < p.n) {
+            if (p.ep_is_f32) {
+              u = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+            } else {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __half*>(p.resid) + static_cast<size_t>(grow) * p.ld_resid + n));
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+              u = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+          }
+          t[rr] = u;
+        }
+      };
+      const bool has_resid = kEpi == EPI_PLAIN && p.resid != nullptr;
+      const uint32_t t_row = tmem_base + acc * kMaxBN + (static_cast<uint32_t>(quad * 32) << 16);
+      // ---- lean path of the fp32 residual stream (the hot case: every to_out / ff.net.2 / conv2 / proj_out
+      // layer): full tile, fp32 result (+ fp32 residual), bias / temb already folded into the staged tables.
+      // No per-element bounds or dtype branches; the next accumulator chunk is requested as soon as the
+      // current one is in registers.
+      if (kEpi == EPI_PLAIN && p.out == nullptr && (p.ep_is_f32 || (p.resid == nullptr && p.temb == nullptr)) &&
+          temb_row == nullptr && tile_row0 + kBM <= p.m && ncol0 + p.bn <= p.n && c_begin < c_end) {
+        const float* resid = static_cast<const float*>(p.resid);
+        const size_t row_a = static_cast<size_t>(warp_row0 + rl0);
+        auto ldres = [&](int c, float4 (&t)[8]) {
+          const float* b = resid + row_a * p.ld_resid + ncol0 + c * 32 + cq;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) t[rr] = __ldg(reinterpret_cast<const float4*>(b + static_cast<size_t>(rr) * 4 * p.ld_resid));
+        };
+        if (has_resid) ldres(c_begin, t_cur);
+        epi_bar_sync<32 * kEpiWarps>();                     // staged tables visible
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c_begin * 32, r);
+        const bool has_rs = p.row_scale != nullptr;
+        for (int c = c_begin; c < c_end; ++c) {
+          const int j0 = c * 32;
+          if (has_resid && c + 1 < c_end) ldres(c + 1, t_nxt);
+          tc_wait_ld();
+          float g[32];
+          if (has_rs) {
+            affine32(r, j0, g);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + j0 + v * 4);
+              const float4 bi = *reinterpret_cast<const float4*>(s_bias + j0 + v * 4);
+              g[v * 4 + 0] = fmaf(__uint_as_float(r[v * 4 + 0]), sc.x, bi.x);
+              g[v * 4 + 1] = fmaf(__uint_as_float(r[v * 4 + 1]), sc.y, bi.y);
+              g[v * 4 + 2] = fmaf(__uint_as_float(r[v * 4 + 2]), sc.z, bi.z);
+              g[v * 4 + 3] = fmaf(__uint_as_float(r[v * 4 + 3]), sc.w, bi.w);
+            }
+          }
+          if (c + 1 < c_end) tmem_ld_32x32(t_row + j0 + 32, r);
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+          __syncwarp();
+          float* o = p.out_f32 + row_a * p.ldc + ncol0 + j0 + cq;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            float4 x = *reinterpret_cast<const float4*>(stg + (rr * 4 + rl0) * kStgLd + cq);
+            if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+            *reinterpret_cast<float4*>(o + static_cast<size_t>(rr) * 4 * p.ldc) = x;
+          }
+          __syncwarp();
+          if (has_resid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      // ---- general plain path: edge tiles, fp16 results, per-row time-embedding rows
+      if (has_resid && c_begin < c_end) load_resid(c_begin, t_cur);
+      epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      for (int c = c_begin; c < c_end; ++c) {
+        uint32_t r[32];
+        const int j0 = c * kUnit;           // first accumulator column of this iteration inside the tile
+        tmem_ld_32x32(t_row + j0, r);
+        if (has_resid && c + 1 < c_end) load_resid(c + 1, t_nxt);
+        float g[32];                        // this thread's row, 32 result columns
+        tc_wait_ld();
+        affine32(r, j0, g);
+        if (temb_row != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = ncol0 + j0 + i;
+            if (n < p.n)
+              g[i] += p.ep_is_f32 ? reinterpret_cast<const float*>(temb_row)[n]
+                                  : __half2float(reinterpret_cast<const __half*>(temb_row)[n]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          *reinterpret_cast<float4*>(stg + lane * kStgLd + v * 4) = make_float4(g[v * 4], g[v * 4 + 1], g[v * 4 + 2], g[v * 4 + 3]);
+        __syncwarp();
+        const int n = ncol0 + j0 + cq;      // result column of this lane's 4 values
+        if (n < p.n) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int rl = rr * 4 + rl0;
+            const int grow = warp_row0 + rl;
+            if (grow < p.m) {
+              float4 x = *reinterpret_cast<const float4*>(stg + rl * kStgLd + cq);
+              if (has_resid) { x.x += t_cur[rr].x; x.y += t_cur[rr].y; x.z += t_cur[rr].z; x.w += t_cur[rr].w; }
+              const size_t o = static_cast<size_t>(grow) * p.ldc + n;
+              if (p.out != nullptr) {
+                const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                *reinterpret_cast<uint2*>(p.out + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              }
+              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + o) = x;
+            }
+          }
+        }
+        __syncwarp();
+        if (has_resid) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      continue;
+      }
       // ---- plain epilogue.  Phase A (thread = row) only moves the raw accumulator chunk TMEM -> registers -> the
       // warp's padded smem tile.  Phase B (lane = 4 columns x every 4th row) does the arithmetic with ITS columns'
       // constants held in registers for the whole chunk and its 8 rows' constants for the whole tile -- the affine,
@@ -641,7 +804,10 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       }
       auto plain = [&](auto full_tag) {
         constexpr bool kFullTile = decltype(full_tag)::value;   // interior tile: no row / column bounds
-        float4 t_cur[8];
+        // kind::f16: the residual segments of the NEXT chunk are prefetched (one-chunk-ahead double buffer); kind::i8
+        // has no registers left for it (its epilogue is not exposed anyway: the MMA time is half)
+        constexpr bool kAhead = !kI8;
+        float4 t_cur[8], t_nxt[kAhead ? 8 : 1];
         auto ldres = [&](int c, float4 (&t)[8]) {
           const int n = ncol0 + c * 32 + cq;
 #pragma unroll
@@ -662,6 +828,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             t[rr] = u;
           }
         };
+        if constexpr (kAhead) {
+          if (has_resid && c_begin < c_end) ldres(c_begin, t_cur);
+        }
         epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -669,9 +838,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (c_begin < c_end) tmem_ld_32x32(t_row + c_begin * 32, r);
         for (int c = c_begin; c < c_end; ++c) {
           const int j0 = c * 32;
-          // the chunk's residual segments are requested before the accumulator wait: their latency is covered by
-          // phase A and by the other epilogue warps (a second, one-chunk-ahead buffer costs 32 registers and spilled)
-          if (has_resid) ldres(c, t_cur);
+          if constexpr (kAhead) {
+            if (has_resid && c + 1 < c_end) ldres(c + 1, reinterpret_cast<float4(&)[8]>(t_nxt));
+          } else {
+            // requested before the accumulator wait: the latency is covered by phase A and the other epilogue warps
+            if (has_resid) ldres(c, t_cur);
+          }
           tc_wait_ld();
 #pragma unroll
           for (int v = 0; v < 8; ++v)
@@ -743,6 +915,12 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
           __syncwarp();
+          if constexpr (kAhead) {
+            if (has_resid) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
+            }
+          }
         }
       };
       // interior tiles with no per-row time-embedding rows take the branch-free instantiation
