@@ -55,6 +55,7 @@ struct AttnDev {
   int nkv, q_tiles, items;
   int nh;                       // 128-row query halves per work item (2: each K/V tile is loaded once for both)
   int nq_buf, nk_buf, nv_buf, no_buf;
+  int ns;                       // S buffers in tensor memory (2, or 3 for the ping-pong pass 2 at dp = 64)
   float alpha;  // scale * log2(e)
   int map_mode, real_time, start_peak;
   const float* delta;
@@ -84,8 +85,8 @@ struct AttnDev {
 // barrier indices (rings of up to 4)
 constexpr int kRing = 4;
 enum { B_QFULL = 0, B_QEMPTY = B_QFULL + kRing, B_KFULL = B_QEMPTY + kRing, B_KEMPTY = B_KFULL + kRing,
-       B_VFULL = B_KEMPTY + kRing, B_VEMPTY = B_VFULL + kRing, B_SFULL = B_VEMPTY + kRing, B_SEMPTY = B_SFULL + 2,
-       B_PFULL = B_SEMPTY + 2, B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_OEMPTY = B_OFULL + 2,
+       B_VFULL = B_KEMPTY + kRing, B_VEMPTY = B_VFULL + kRing, B_SFULL = B_VEMPTY + kRing, B_SEMPTY = B_SFULL + 3,
+       B_PFULL = B_SEMPTY + 3, B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_OEMPTY = B_OFULL + 2,
        B_COUNT = B_OEMPTY + 2 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -213,7 +214,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     prefetch_tmap(&tm_k);
     if (PASS == 2) prefetch_tmap(&tm_v);
     for (int i = 0; i < B_COUNT; ++i) {
-      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2) ||
+      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 3) || (i >= B_PFULL && i < B_PFULL + 2) ||
                           (i >= B_OEMPTY && i < B_OEMPTY + 2);
       mbar_init(&bars[i], all_sm ? (PP ? kSoftmaxWarps / 2 : kSoftmaxWarps) : 1);
     }
@@ -228,7 +229,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  // score buffers: step U uses S[U % ns].  ns = 3 (ping-pong pass 2, dp = 64: 3 x 128 + 2 x 64 = 512 columns) lets the
+  // QK^T of a group's NEXT tile start before that group has drained the current one -- with one buffer per group the
+  // issuer waited for SEMPTY half of the time and the softmax warps for SFULL a quarter of theirs (ncu, round 2)
+  const uint32_t ns = p.ns;
+  const uint32_t tmem_o = tmem_base + ns * kTileK;
   const int q_groups = (p.q_tiles + static_cast<int>(nh) - 1) / static_cast<int>(nh);   // items per (batch, head)
 
   // Sequence numbers shared by all roles (each role counts them itself):
@@ -348,9 +353,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
             const uint32_t slot0 = (g * kparts) % nkb, slot1 = (g * kparts + kparts - 1) % nkb;
             for (uint32_t h = 0; h < nh; ++h) {
-              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu & 1;
+              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu % ns;
               if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
-              mbar_wait(&bars[B_SEMPTY + sb], ((uu >> 1) & 1) ^ 1);
+              mbar_wait(&bars[B_SEMPTY + sb], ((uu / ns) & 1) ^ 1);
               tc_fence_after();
               const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot0 * qstep, db1 = dk0 + slot1 * qstep;
               const uint32_t d_s = tmem_base + sb * kTileK;
@@ -383,10 +388,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const uint32_t gp = g * kparts + part, slot = gp % nkb;
             mbar_wait(&bars[B_KFULL + slot], (gp / nkb) & 1);
             for (uint32_t h = 0; h < nh; ++h) {
-              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu & 1;
+              const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu % ns;
               if (part == 0) {
                 if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
-                mbar_wait(&bars[B_SEMPTY + sb], ((uu >> 1) & 1) ^ 1);
+                mbar_wait(&bars[B_SEMPTY + sb], ((uu / ns) & 1) ^ 1);
               }
               tc_fence_after();
               const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot * qstep;
@@ -573,14 +578,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int dd = etid; dd < p.dp; dd += kGroupThreads)
             v0[dd] = __half2float(p.vt[(static_cast<size_t>(bh) * p.dp + dd) * p.sp]);
         }
-        const uint32_t sb = grp;
+        const uint32_t pbuf = grp;                // the group's P' buffer and O accumulator
         const int s_len = (CODES && !rok) ? 0 : p.s;
         uint8_t* code_row = CODES ? p.codes + rix * p.s : nullptr;
         // this thread's 64 score columns are one [128 x 64] SW128 sub-tile of the P' buffer
-        const uint32_t sub = sp_base + sb * 2 * kChunkBytes + half * kChunkBytes;
+        const uint32_t sub = sp_base + pbuf * 2 * kChunkBytes + half * kChunkBytes;
         for (int j = 0; j < p.nkv; ++j, ++u) {
-          const uint32_t ph = u & 1;
-          mbar_wait(&bars[B_SFULL + sb], ph);
+          const uint32_t ph = u & 1;              // phase of the group's P' buffer
+          const uint32_t uu = 2 * u + grp, sb = uu % ns;   // CTA-wide step number -> its S buffer
+          mbar_wait(&bars[B_SFULL + sb], (uu / ns) & 1);
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -599,7 +605,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 p0 = ex2_approx(fmaf(alpha, __uint_as_float(r[0]), -beta));
                 h2[0] &= 0xFFFF0000u;             // column 0 leaves the MMA; added back in the epilogue
               }
-              mbar_wait(&bars[B_PEMPTY + sb], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
+              mbar_wait(&bars[B_PEMPTY + pbuf], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
             }
 #pragma unroll
             for (int v = 0; v < 4; ++v)
@@ -607,7 +613,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
+          if (lane == 0) mbar_arrive(&bars[B_PFULL + pbuf]);
         }
         // ---- epilogue of this group's half; the other group keeps the tensor pipe busy meanwhile
         float pp0 = p0;
@@ -852,6 +858,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
     p.nv_buf = 1;                                   // Q 4 + K 4 + V 1 + P' 4 = 208 KB)
   }
   p.no_buf = a->dp <= 128 ? 2 : 1;
+  p.ns = (p.nh == 2 && a->dp <= 64) ? 3 : 2;
   p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
   p.alpha = a->scale * 1.4426950408889634f;
   p.map_mode = a->map_mode; p.real_time = a->real_time; p.start_peak = a->start_peak;
@@ -874,8 +881,9 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
 
   const uint32_t q_bytes = (a->dp / 64) * kChunkBytes;
   const uint32_t tail = 1024 + B_COUNT * 8 + 16 + 4 * 192 * 4 + 3 * 128 * 4 + 64;
-  AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring
+  AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring, 256 TMEM columns
   if (p1.nq_buf > 2) p1.nq_buf = 2;
+  p1.ns = 2;
   const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
   const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);

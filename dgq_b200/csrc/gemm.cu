@@ -46,7 +46,9 @@ constexpr int kStgLd = 36;                         // padded row stride (floats)
 constexpr int kEpiTab = 9;                         // per-column tables staged per tile
 constexpr int kRsRing = 8;                         // kI8: ring of per-tile row-sum vectors (row-sum warps run ahead)
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
-template <int kEpi, bool kI8 = false> struct EpiCfg {
+template <int kEpi, bool kI8 = false, int kCtas = 2> struct EpiCfg {
+  // (16 warps were measured for the kind::i8 plain epilogue too: slower -- it is bound by LSU wavefronts and
+  // instruction issue, not by latency; profiles/r2_gemm_epilogue_digest.txt)
   static constexpr int kWarps = kEpi == EPI_PLAIN ? 8 : 16;
   static constexpr int kThreads = 64 + 32 * kWarps + (kI8 ? 32 : 0);   // kI8: + the row-sum warp
   static constexpr int kSplit = kWarps / 4;        // column splits of a tile (one per warp of a lane quarter)
@@ -68,7 +70,7 @@ template <int kCtas, int kEpi, bool kI8 = false> struct GemmCfg {
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // [2 buffers][scale | bias | q.delta | 1/q.delta | -q.zp | qmax - q.zp][256] fp32 + one [32 rows][36] fp32 transpose
   // buffer per epilogue warp
-  static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + EpiCfg<kEpi>::kWarps * EpiCfg<kEpi>::kStgBytes;
+  static constexpr uint32_t kEpiBytes = 2 * kEpiTab * kMaxBN * 4 + EpiCfg<kEpi, kI8, kCtas>::kWarps * EpiCfg<kEpi, kI8, kCtas>::kStgBytes;
   static constexpr uint32_t kRsBytes = kI8 ? kRsRing * kBM * 4 : 0;
   static constexpr uint32_t kSmem = kStages * kStageBytes + kEpiBytes + kRsBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
@@ -120,14 +122,14 @@ template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the
 // MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
 // L2->smem bytes of the single-CTA tile.
 template <int kCtas, int kEpi, bool kI8>
-__global__ void __launch_bounds__(EpiCfg<kEpi, kI8>::kThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<kEpi, kI8, kCtas>::kThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
   using Cfg = GemmCfg<kCtas, kEpi, kI8>;
   constexpr int kBKe = kI8 ? 2 * kBK : kBK;      // K elements per 128-byte stage row
   constexpr int kStages = Cfg::kStages;
-  constexpr int kEpiWarps = EpiCfg<kEpi>::kWarps;
-  constexpr int kSplit = EpiCfg<kEpi>::kSplit;
+  constexpr int kEpiWarps = EpiCfg<kEpi, kI8, kCtas>::kWarps;
+  constexpr int kSplit = EpiCfg<kEpi, kI8, kCtas>::kSplit;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as an OFFSET from the __shared__ base: the pointer keeps its address space, so the
   // epilogue / softmax accesses compile to LDS / STS instead of generic LD / ST
@@ -327,7 +329,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int c_end = (nch * (split + 1) + kSplit - 1) / kSplit;
     const bool temb_tile = p.temb != nullptr && (p.rows_per_batch % (kBM * kCtas)) == 0;
     float* stg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_epi + 2 * kEpiTab * kMaxBN) +
-                                          (warp - 2) * EpiCfg<kEpi>::kStgBytes);
+                                          (warp - 2) * EpiCfg<kEpi, kI8, kCtas>::kStgBytes);
     const int rl0 = lane >> 3;          // row (0..3) inside a group of 4 rows
     const int cq = (lane & 7) * 4;      // first of this lane's 4 columns inside the chunk
     const EpiQuant& q2 = p.q2;
@@ -802,12 +804,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         *reinterpret_cast<uint4*>(stg + lane * kStgLd + 32) =
             make_uint4(__float_as_uint(ra), static_cast<uint32_t>(nz), static_cast<uint32_t>(rp), static_cast<uint32_t>(my_cls));
       }
+      // (a variant that folds a scalar activation quantizer's -za * colsum_n and delta_a * delta_w[n] once per chunk
+      // was measured on the epilogue-only probe: 314 us against 227 us -- dropped)
       auto plain = [&](auto full_tag) {
         constexpr bool kFullTile = decltype(full_tag)::value;   // interior tile: no row / column bounds
-        // kind::f16: the residual segments of the NEXT chunk are prefetched (one-chunk-ahead double buffer); kind::i8
-        // has no registers left for it (its epilogue is not exposed anyway: the MMA time is half)
-        constexpr bool kAhead = !kI8;
-        float4 t_cur[8], t_nxt[kAhead ? 8 : 1];
+        float4 t_cur[8];
         auto ldres = [&](int c, float4 (&t)[8]) {
           const int n = ncol0 + c * 32 + cq;
 #pragma unroll
@@ -828,9 +829,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             t[rr] = u;
           }
         };
-        if constexpr (kAhead) {
-          if (has_resid && c_begin < c_end) ldres(c_begin, t_cur);
-        }
         epi_bar_sync<32 * kEpiWarps>();                       // staged tables visible
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -838,12 +836,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         if (c_begin < c_end) tmem_ld_32x32(t_row + c_begin * 32, r);
         for (int c = c_begin; c < c_end; ++c) {
           const int j0 = c * 32;
-          if constexpr (kAhead) {
-            if (has_resid && c + 1 < c_end) ldres(c + 1, reinterpret_cast<float4(&)[8]>(t_nxt));
-          } else {
-            // requested before the accumulator wait: the latency is covered by phase A and the other epilogue warps
-            if (has_resid) ldres(c, t_cur);
-          }
+          // requested before the accumulator wait: the latency is covered by phase A and the other epilogue warps
+          if (has_resid) ldres(c, t_cur);
           tc_wait_ld();
 #pragma unroll
           for (int v = 0; v < 8; ++v)
@@ -915,12 +909,6 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
           }
           __syncwarp();
-          if constexpr (kAhead) {
-            if (has_resid) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) t_cur[i] = t_nxt[i];
-            }
-          }
         }
       };
       // interior tiles with no per-row time-embedding rows take the branch-free instantiation
@@ -1017,7 +1005,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
     attr.mark(dev);
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  constexpr int kGemmThreads = EpiCfg<kEpi, kI8>::kThreads;
+  constexpr int kGemmThreads = EpiCfg<kEpi, kI8, kCtas>::kThreads;
   if (kCtas == 1) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     gemm_f16_kernel<kCtas, kEpi, kI8><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi, kI8>::kSmem, s>>>(ta, tb, p);
