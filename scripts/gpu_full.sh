@@ -18,6 +18,7 @@ ncu -i gpurun_out/r2_gemm_final.ncu-rep --page raw --csv \
   --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.sum \
   > gpurun_out/r2_gemm_final_dram.csv 2>&1
 cat gpurun_out/r2_gemm_final_dram.csv | cut -c1-600
+python scripts/make_gemm_traffic.py gpurun_out/r2_gemm_final_dram.csv gpurun_out/r2_gemm_traffic.json
 echo "== bench default (config 4, CPU legs)"
 timeout 1200 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 tail -c 600 gpurun_out/r2_bench_default.json
