@@ -12,7 +12,7 @@ SYMBOLS = [
     "dgq_version", "dgq_fake_quant_f32", "dgq_t2i_log_quant_f32", "dgq_max_f32", "dgq_pack_weight", "dgq_unpack_weight",
     "dgq_act_producer", "dgq_gn_stats", "dgq_ln_quant", "dgq_row_quant", "dgq_geglu_quant",
     "dgq_gemm_f16", "dgq_gemm_i8", "dgq_weight_to_i8", "dgq_conv_oob_colsum", "dgq_qkv_pack", "dgq_attention", "dgq_timestep_embedding", "dgq_nchw_to_nhwc",
-    "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add", "dgq_sampler_step",
+    "dgq_nhwc_to_nchw", "dgq_silu", "dgq_add", "dgq_softmax_rows", "dgq_sampler_step",
 ]
 
 Q_NONE, Q_SCALAR, Q_KWISE, Q_ROWWISE = 0, 1, 2, 3
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
             "dgq_nchw_to_nhwc": [vp, i, i, i, i, vp, i, vp],
             "dgq_nhwc_to_nchw": [vp, i, i, i, i, i, vp, vp],
             "dgq_silu": [vp, i, i64, vp, vp],
+            "dgq_softmax_rows": [vp, i64, i, i64, f, vp, i64, vp],
             "dgq_add": [vp, vp, i, i64, vp, vp],
             "dgq_sampler_step": [C.POINTER(SamplerStepT), vp],
         }

@@ -1062,6 +1062,65 @@ extern "C" int dgq_nhwc_to_nchw(const void* x, int src_is_f32, int b, int c, int
   else nhwc_to_nchw_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half*>(x), b, c, hw, ldx, out);
   DGQ_RETURN_LAST_ERROR();
 }
+// ---------------------------------------------------------------------------------------------
+// P[r, :] = softmax(scale * S[r, :]) as fp16: the attention map of the VAE decoder's single-head mid-block attention
+// (F.scaled_dot_product_attention at diffusers/models/attention_processor.py:1244; head dim 512 does not fit the
+// TMEM-resident flash kernel, and the block runs once per image).  One CTA per row; the row is read three times
+// (max, sum, write) -- the 2nd and 3rd reads hit L1 / L2.
+namespace dgq {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int cols, int64_t lds,
+                                                            float scale_log2e, __half* __restrict__ out, int64_t ldo) {
+  __shared__ float red[8];
+  const float4* row = reinterpret_cast<const float4*>(s + static_cast<int64_t>(blockIdx.x) * lds);
+  const int n4 = cols >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -3.0e38f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = __ldg(row + i);
+    m = fmaxf(fmaxf(fmaxf(m, v.x), fmaxf(v.y, v.z)), v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float mb = m * scale_log2e;
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = __ldg(row + i);
+    sum += exp2f(fmaf(v.x, scale_log2e, -mb)) + exp2f(fmaf(v.y, scale_log2e, -mb)) +
+           exp2f(fmaf(v.z, scale_log2e, -mb)) + exp2f(fmaf(v.w, scale_log2e, -mb));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  uint2* orow = reinterpret_cast<uint2*>(out + static_cast<int64_t>(blockIdx.x) * ldo);
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 v = __ldg(row + i);
+    const __half2 a = __floats2half2_rn(exp2f(fmaf(v.x, scale_log2e, -mb)) * inv, exp2f(fmaf(v.y, scale_log2e, -mb)) * inv);
+    const __half2 b = __floats2half2_rn(exp2f(fmaf(v.z, scale_log2e, -mb)) * inv, exp2f(fmaf(v.w, scale_log2e, -mb)) * inv);
+    orow[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+}  // namespace dgq
+
+extern "C" int dgq_softmax_rows(const float* s, int64_t rows, int cols, int64_t lds, float scale, void* out_f16,
+                                int64_t ldo, void* stream) {
+  DGQ_CHECK_ARG(s != nullptr && out_f16 != nullptr && rows > 0 && rows < (1ll << 31) && cols > 0 && cols % 4 == 0);
+  DGQ_CHECK_ARG(lds >= cols && lds % 4 == 0 && ldo >= cols && ldo % 4 == 0);
+  DGQ_CHECK_ARG((reinterpret_cast<uintptr_t>(s) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 7) == 0);
+  dgq::softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      s, cols, lds, scale * 1.4426950408889634f, static_cast<__half*>(out_f16), ldo);
+  DGQ_RETURN_LAST_ERROR();
+}
+
 extern "C" int dgq_silu(const void* x, int is_f32, int64_t n, void* out, void* stream) {
   using namespace dgq;
   DGQ_CHECK_ARG(x != nullptr && out != nullptr && n > 0);

@@ -422,6 +422,18 @@ def silu(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> fp16 softmax(scale * s) along the rows (VAE mid-block attention map)"""
+    if s.dtype != torch.float32 or s.dim() != 2 or s.stride(1) != 1:
+        raise TypeError("softmax_rows: fp32 row-major matrix expected")
+    if out is None:
+        out = torch.empty(s.shape, dtype=torch.float16, device=s.device)
+    L.check(L.lib().dgq_softmax_rows(_p(s), s.shape[0], s.shape[1], s.stride(0), float(scale), _p(out), out.stride(0),
+                                     _stream()), "dgq_softmax_rows")
+    _count()
+    return out
+
+
 def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(a)
     if a.dtype != b.dtype:

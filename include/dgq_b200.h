@@ -275,6 +275,11 @@ int dgq_nchw_to_nhwc(const float* x, int b, int c, int hw, int c_pad, void* out,
 int dgq_nhwc_to_nchw(const void* x, int src_is_f32, int b, int c, int hw, int ldx, float* out, void* stream);
 /* y = silu(x) elementwise (SiLU on the time embedding, quant/quant_block.py:107); fp16 or fp32  */
 int dgq_silu(const void* x, int is_f32, int64_t n, void* out, void* stream);
+/* P[r, :] = softmax(scale * S[r, :]), fp32 [rows, lds] -> fp16 [rows, ldo]: the attention map of the VAE decoder's
+ * mid-block attention (F.scaled_dot_product_attention, diffusers/src/diffusers/models/attention_processor.py:1244;
+ * one head of 512 channels), between two dgq_gemm_f16 calls.  cols % 4 == 0.                     */
+int dgq_softmax_rows(const float* s, int64_t rows, int cols, int64_t lds, float scale, void* out_f16, int64_t ldo,
+                     void* stream);
 /* out = a + b; fp16 or fp32                                                                     */
 int dgq_add(const void* a, const void* b, int is_f32, int64_t n, void* out, void* stream);
 

@@ -1,16 +1,20 @@
-"""Latent-space counterpart of the reference's src/inference_qmodel.py: same quantization
-flags, the quantized UNet + the device sampler loop, no text encoder / VAE (neither is in scope, and no
-pretrained weights exist offline).
+"""Counterpart of the reference's src/inference_qmodel.py: same quantization flags, the
+quantized UNet + the device sampler loop + (optionally) the VAE decode and the PNG files the reference writes
+(src/inference_qmodel.py:46-53).  The text encoders stay outside: prompt embeddings come from a file or a seeded draw
+(no pretrained weights exist offline).
 
   DIFFUSERS_REWRITE=sdxl python scripts/inference_qmodel.py --cali_ckpt ckpt_merged.pth --wq 4 --use_aq --aq 8 \
       --use_group --t2i_log_quant --t2i_real_time --t2i_start_peak --time_aware_aqtizer \
       [--num_inference_steps N] [--prompt_embeds embeds.pt] [--batch 2] [--out latents.pt]
   ... --compiled unet.dgqb          # a dgq_b200 compiled checkpoint instead of --cali_ckpt (flags come from its header)
   ... --synthetic                   # random-init weights + synthetic scales (no checkpoint at all)
+  ... --vae vae_state.pt --outdir imgs      # decode with a diffusers AutoencoderKL state dict and save PNGs
+  ... --synthetic_vae --outdir imgs         # the same path on random-init decoder weights
 
 `--prompt_embeds`: a torch file {"ctx": [B,77,C]} (SD: the cond embeddings; the uncond half {"uncond": ...} is
 optional, zeros otherwise) or, for SDXL, {"ctx": [B,77,2048], "text_embeds": [B,1280]}; omitted => N(0,1) draws
-with --seed.  Writes the final latents (fp32, [B,4,h,w]); feed them to the reference's VAE to get images.
+with --seed.  Writes the final latents (fp32, [B,4,h,w]) and, with --vae / --synthetic_vae, the decoded images as
+tmp_{model_type}_{i}_{precision}.png (the reference's naming without the prompt text).
 Defaults follow the reference: 25 PLMS steps + CFG 7.5 for sd, 4 Euler-ancestral steps, guidance 0 for sdxl."""
 import argparse
 import os
@@ -42,7 +46,33 @@ def parse_args():
     p.add_argument("--batch", type=int, default=2, help="images (the reference runs [prompt] * 2)")
     p.add_argument("--guidance", type=float, default=None)
     p.add_argument("--out", type=str, default=None)
+    p.add_argument("--vae", type=str, default=None, help="AutoencoderKL state dict (torch.save / safetensors): decode + save PNGs")
+    p.add_argument("--synthetic_vae", action="store_true", help="random-init VAE decoder weights (path check only)")
+    p.add_argument("--outdir", type=str, default=".")
     return p.parse_args()
+
+
+def build_vae(opt):
+    """dgq_b200.vae.VaeDecoder with the stabilityai sd-vae / sdxl-vae decoder architecture"""
+    import torch
+    from dgq_b200.vae import VaeDecoder
+    vae = VaeDecoder(scaling_factor=0.18215 if MODEL_TYPE == "sd" else 0.13025)
+    if opt.vae:
+        if opt.vae.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            sd = load_file(opt.vae)
+        else:
+            sd = torch.load(opt.vae, map_location="cpu")
+        res = vae.load_state_dict(sd, strict=False)
+        if res.missing_keys:
+            raise SystemExit(f"--vae: {len(res.missing_keys)} decoder tensors missing, e.g. {res.missing_keys[:3]}")
+    else:
+        g = torch.Generator().manual_seed(opt.seed)
+        with torch.no_grad():
+            for prm in vae.parameters():
+                if prm.dim() > 1:
+                    prm.copy_((torch.rand(prm.shape, generator=g) * 2 - 1) / (prm[0].numel() ** 0.5))
+    return vae.cuda().eval()
 
 
 def build_qnn(opt, n_steps):
@@ -107,6 +137,16 @@ def main():
     t_run = time.time() - t1
     out = opt.out or f"latents_{MODEL_TYPE}_w{opt.wq}a{opt.aq if opt.use_aq else 32}_{n_steps}steps.pt"
     torch.save({"latents": x.float().cpu(), "model_type": MODEL_TYPE, "steps": n_steps, "seed": opt.seed}, out)
+    if opt.vae or opt.synthetic_vae:
+        from dgq_b200 import vae as vae_mod
+        vae = build_vae(opt)
+        t2 = time.time()
+        img = vae.decode_latents(x.float())             # pipeline_stable_diffusion.py:1066-1069 / _xl.py:1295-1307
+        u8 = vae_mod.postprocess(img)
+        torch.cuda.synchronize()
+        precision = f"w{opt.wq}a{opt.aq if opt.use_aq else 32}{'g?' if opt.use_group else 'g1'}"
+        paths = vae_mod.save_images(u8, opt.outdir, prefix=f"tmp_{MODEL_TYPE}_{precision}")
+        print(f"vae decode {tuple(img.shape)} {time.time() - t2:.2f} s -> {paths[0]} ... ({len(paths)} files)")
     print(f"{MODEL_TYPE}: load {t_load:.1f} s, {n_steps}-step loop for {b} images {t_run:.2f} s (incl. graph capture), "
           f"latents {tuple(x.shape)} finite={bool(torch.isfinite(x).all())} -> {out}")
 

@@ -6,6 +6,7 @@ copy):
     python tests/golden/make_golden.py ops          # op-level vectors  -> ops.pt
     python tests/golden/make_golden.py unet sd      # full-UNet latents -> unet_sd_*.pt
     python tests/golden/make_golden.py unet sdxl [case]   # one case per process keeps peak RSS < 60 GB
+    python tests/golden/make_golden.py vae          # AutoencoderKL.decode + image postprocess -> vae.pt
 
 Inputs are regenerated from seeds by the tests (oracle/synth.py uses numpy
 PCG64 / torch CPU generators, both machine-independent), so only the
@@ -282,8 +283,49 @@ def make_unet(model_type, only=None):
         torch.save({"outs": outs, "case": UNET_CASES[case]}, f"{OUT}/unet_{model_type}_{case}.pt")
 
 
+VAE_CASES = {   # name -> (config of oracle.vae_oracle.VAE_CONFIGS, latent batch, latent size, weight seed, input seed)
+    "small_b2_16": ("small", 2, 16, 0, 1),
+    "sd_b1_8": ("sd", 1, 8, 0, 2),
+    "sdxl_b1_8": ("sdxl", 1, 8, 3, 4),
+}
+
+
+def make_vae():
+    """The reference's own AutoencoderKL (vendored diffusers) on weights synthesised by oracle.vae_oracle: the
+    pipelines' `vae.decode(latents / scaling_factor)` and `VaeImageProcessor.postprocess`."""
+    torch, O, S = import_reference("sd")
+    import importlib
+    V = importlib.import_module("oracle_pkg.vae_oracle")
+    from diffusers.models.autoencoders.autoencoder_kl import AutoencoderKL
+    from diffusers.image_processor import VaeImageProcessor
+    gold = {}
+    for name, (cfgname, b, size, wseed, iseed) in VAE_CASES.items():
+        cfg = V.VAE_CONFIGS[cfgname]
+        n = len(cfg["block_out_channels"])
+        vae = AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * n,
+                            up_block_types=("UpDecoderBlock2D",) * n, block_out_channels=cfg["block_out_channels"],
+                            layers_per_block=cfg["layers_per_block"], latent_channels=cfg["latent_channels"],
+                            norm_num_groups=32, sample_size=size * 8, scaling_factor=cfg["scaling_factor"]).eval()
+        sd = V.make_vae_state(cfg, wseed)
+        want = {k for k in vae.state_dict() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
+        assert want == set(sd), (sorted(want - set(sd))[:5], sorted(set(sd) - want)[:5])
+        print(name, vae.load_state_dict(sd, strict=False).unexpected_keys)
+        g = torch.Generator().manual_seed(iseed)
+        lat = torch.randn(b, cfg["latent_channels"], size, size, generator=g) * cfg["scaling_factor"] * 4.0
+        with torch.no_grad():
+            img = vae.decode(lat / vae.config.scaling_factor, return_dict=False)[0]
+        proc = VaeImageProcessor(vae_scale_factor=2 ** (n - 1))
+        np_img = proc.postprocess(img, output_type="np")
+        u8 = torch.from_numpy((np_img * 255).round().astype("uint8"))          # numpy_to_pil's conversion
+        gold[name] = {"case": VAE_CASES[name], "latents": lat, "image": img.clone(), "u8": u8}
+        print(name, tuple(img.shape), float(img.abs().mean()), float(u8.float().mean()))
+    torch.save(gold, f"{OUT}/vae.pt")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "ops":
         make_ops()
+    elif sys.argv[1] == "vae":
+        make_vae()
     else:
         make_unet(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

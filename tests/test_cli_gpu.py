@@ -29,3 +29,13 @@ def test_cli_synthetic_sd_loop(tmp_path):
     # same seed, same flags: bit-identical (deterministic kernels, graph replay)
     r2 = _run(["--synthetic", *FLAGS], tmp_path, "b.pt")
     assert torch.equal(x, r2["latents"])
+
+
+def test_cli_decodes_and_saves_images(tmp_path):
+    """--synthetic_vae: the loop's latents go through dgq_b200.vae.VaeDecoder and come out as PNG files"""
+    from PIL import Image
+    r = _run(["--synthetic", "--synthetic_vae", "--outdir", str(tmp_path / "imgs"), *FLAGS], tmp_path, "c.pt")
+    files = sorted(os.listdir(tmp_path / "imgs"))
+    assert len(files) == r["latents"].shape[0] == 1 and files[0].endswith(".png")
+    im = Image.open(tmp_path / "imgs" / files[0])
+    assert im.size == (512, 512) and im.mode == "RGB"

@@ -237,3 +237,16 @@ def test_cli_accepts_the_reference_flags(monkeypatch):
     monkeypatch.setattr("sys.argv", ["prog"])
     d = cli.parse_args()       # the reference's defaults
     assert (d.wq, d.aq, d.seed, d.num_inference_steps, d.use_aq, d.use_group) == (4, 8, 42, -1, False, False)
+
+
+def test_vae_decoder_schema_matches_the_reference_state_dict():
+    """dgq_b200.vae.VaeDecoder holds exactly the `post_quant_conv.*` / `decoder.*` keys and shapes of the reference's
+    AutoencoderKL (enumerated by oracle.vae_oracle, which tests/golden/make_golden.py loads into the reference)."""
+    from dgq_b200.vae import VaeDecoder
+    from oracle import vae_oracle as V
+    for name in ("sd", "small"):
+        cfg = V.VAE_CONFIGS[name]
+        ref = V.make_vae_state(cfg, 0)
+        mine = VaeDecoder(cfg["block_out_channels"], cfg["layers_per_block"], cfg["latent_channels"]).state_dict()
+        assert set(mine) == set(ref)
+        assert all(tuple(mine[k].shape) == tuple(ref[k].shape) for k in ref)
