@@ -44,7 +44,7 @@ constexpr int kMaxBN = 256;
 constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KB
 constexpr int kStgLd = 36;                         // padded row stride (floats) of the fp32 epilogue transpose buffer
 constexpr int kEpiTab = 9;                         // per-column tables staged per tile
-constexpr int kRsRing = 8;                         // kI8: ring of per-tile row-sum vectors (row-sum warps run ahead)
+constexpr int kRsRing = 16;                        // kI8: ring of per-tile row-sum vectors (the row-sum warp runs at most 2 + kStages tiles ahead)
 enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_QKV = 2 };
 template <int kEpi, bool kI8 = false, int kCtas = 2> struct EpiCfg {
   // (16 warps were measured for the kind::i8 plain epilogue too: slower -- it is bound by LSU wavefronts and
@@ -64,9 +64,13 @@ struct EpiQuant {   // quantizer applied by the fused epilogues (the NEXT op's a
   int emit_int;
 };
 
-template <int kCtas, int kEpi, bool kI8 = false> struct GemmCfg {
-  static constexpr int kStages = kCtas == 1 ? 3 : 5;
-  static constexpr uint32_t kBBytes = (kMaxBN / kCtas) * kBK * 2;  // 32 KB, or 16 KB per CTA of a pair
+// kSmall (single CTA only): N tile <= 64 columns and a 6-deep ring.  Small-M problems (batch 1: a handful of tiles,
+// K up to 23040) are one long latency chain per CTA -- a k-block took ~0.55 us with 3 stages in flight whatever the
+// tile width; narrower tiles put 4x the CTAs to work and the deeper ring doubles the bytes each keeps in flight.
+constexpr int kSmallBN = 64;
+template <int kCtas, int kEpi, bool kI8 = false, bool kSmall = false> struct GemmCfg {
+  static constexpr int kStages = kSmall ? 6 : (kCtas == 1 ? 3 : 5);
+  static constexpr uint32_t kBBytes = (kSmall ? kSmallBN : kMaxBN / kCtas) * kBK * 2;  // 32 KB, 16 KB per CTA of a pair, 8 KB small
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   // [2 buffers][scale | bias | q.delta | 1/q.delta | -q.zp | qmax - q.zp][256] fp32 + one [32 rows][36] fp32 transpose
   // buffer per epilogue warp
@@ -121,11 +125,11 @@ template <int kThreads> __device__ __forceinline__ void epi_bar_sync() {  // the
 // 256 x bn tile -- each CTA stages its own 128 rows of A and bn/2 rows of B, the leader issues the
 // MMAs for both, each CTA drains its own 128 accumulator rows.  Per FLOP this moves 2/3 of the
 // L2->smem bytes of the single-CTA tile.
-template <int kCtas, int kEpi, bool kI8>
+template <int kCtas, int kEpi, bool kI8, bool kSmall = false>
 __global__ void __launch_bounds__(EpiCfg<kEpi, kI8, kCtas>::kThreads, 1)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const GemmDev p) {
-  using Cfg = GemmCfg<kCtas, kEpi, kI8>;
+  using Cfg = GemmCfg<kCtas, kEpi, kI8, kSmall>;
   constexpr int kBKe = kI8 ? 2 * kBK : kBK;      // K elements per 128-byte stage row
   constexpr int kStages = Cfg::kStages;
   constexpr int kEpiWarps = EpiCfg<kEpi, kI8, kCtas>::kWarps;
@@ -994,13 +998,13 @@ static int pick_bn(int n, int step) {
   return best;
 }
 
-template <int kCtas, int kEpi, bool kI8>
+template <int kCtas, int kEpi, bool kI8, bool kSmall = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, cudaStream_t s) {
   static PerDeviceOnce attr;       // per instantiation, per device
   int dev;
   if (!attr.done(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi, kI8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<kCtas, kEpi, kI8>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16_kernel<kCtas, kEpi, kI8, kSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmCfg<kCtas, kEpi, kI8, kSmall>::kSmem);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr.mark(dev);
   }
@@ -1008,13 +1012,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   constexpr int kGemmThreads = EpiCfg<kEpi, kI8, kCtas>::kThreads;
   if (kCtas == 1) {
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_f16_kernel<kCtas, kEpi, kI8><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi, kI8>::kSmem, s>>>(ta, tb, p);
+    gemm_f16_kernel<kCtas, kEpi, kI8, kSmall><<<grid, kGemmThreads, GemmCfg<kCtas, kEpi, kI8, kSmall>::kSmem, s>>>(ta, tb, p);
   } else {
     const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
-    cfg.dynamicSmemBytes = GemmCfg<kCtas, kEpi, kI8>::kSmem;
+    cfg.dynamicSmemBytes = GemmCfg<kCtas, kEpi, kI8, kSmall>::kSmem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1023,7 +1027,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtas, kEpi, kI8>, ta, tb, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_f16_kernel<kCtas, kEpi, kI8, kSmall>, ta, tb, p);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   DGQ_RETURN_LAST_ERROR();
@@ -1096,6 +1100,19 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
   int ctas = (a->m > kBM && ((a->m + 2 * kBM - 1) / (2 * kBM)) * p.n_tiles >= kNumSMs / 2) ? 2 : 1;
   if (force_ctas == 1 || force_ctas == 2) ctas = force_ctas;
   p.m_tiles = (a->m + kBM * ctas - 1) / (kBM * ctas);
+  // few tiles and a long reduction (the batch-1 UNet: 1-10 tiles, K up to 23040): 64-column tiles on a 6-deep ring
+  static int small_on = -1;     // DGQ_GEMM_SMALL=0 switches the variant off (A/B runs)
+  if (small_on < 0) {
+    const char* env = getenv("DGQ_GEMM_SMALL");
+    small_on = (env == nullptr || atoi(env) != 0) ? 1 : 0;
+  }
+  const int kb_total = (a->k + (i8 ? 2 * kBK : kBK) - 1) / (i8 ? 2 * kBK : kBK);
+  const bool small = small_on && ctas == 1 && force_bn <= 0 && p.bn > kSmallBN && p.m_tiles * p.n_tiles * 2 <= kNumSMs &&
+                     kb_total >= 4 && a->n >= kSmallBN;
+  if (small) {
+    p.bn = kSmallBN;
+    p.n_tiles = (a->n + p.bn - 1) / p.bn;
+  }
   p.scale = a->scale; p.bias = a->bias;
   p.row_scale = a->row_scale; p.row_period = a->row_period > 0 ? a->row_period : 1;
   p.temb = a->temb;
@@ -1131,6 +1148,16 @@ static int gemm_dispatch(const dgq_gemm_t* a, void* stream, bool i8) {
   if (rc != 0) return rc;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (small) {
+    if (i8) {
+      if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU, true, true>(ta, tb, p, s);
+      if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV, true, true>(ta, tb, p, s);
+      return launch_gemm<1, EPI_PLAIN, true, true>(ta, tb, p, s);
+    }
+    if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU, false, true>(ta, tb, p, s);
+    if (a->epi == DGQ_EPI_QKV) return launch_gemm<1, EPI_QKV, false, true>(ta, tb, p, s);
+    return launch_gemm<1, EPI_PLAIN, false, true>(ta, tb, p, s);
+  }
   if (i8) {
     if (ctas == 1) {
       if (a->epi == DGQ_EPI_GEGLU) return launch_gemm<1, EPI_GEGLU, true>(ta, tb, p, s);

@@ -16,7 +16,8 @@ def _scales(g, n, level):
     return d, torch.round(-lo / d)
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 256, 128), (300, 200, 320), (1000, 1280, 1280), (4096, 320, 2880), (77, 640, 2048)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 128), (300, 200, 320), (1000, 1280, 1280), (4096, 320, 2880), (77, 640, 2048),
+                                   (64, 1280, 11520), (1, 1280, 1280), (256, 1288, 2304)])   # the last three: 64-column tiles, 6-deep ring
 @pytest.mark.parametrize("wbits", [4, 8])
 @pytest.mark.parametrize("rowwise", [False, True])
 def test_gemm_i8_exact(m, n, k, wbits, rowwise):
