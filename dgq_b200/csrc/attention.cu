@@ -32,17 +32,25 @@
 
 namespace dgq {
 
+
 // warp 0 loader, warp 1 MMA, then the softmax warps: 8 in pass 1 (thread = row x 64-column half; the pass
 // is MUFU-bound and two CTAs share an SM), 16 in pass 2 (thread = row x 32-column quarter; one CTA per
 // SM, and the ALU-only map needs 4 warps per scheduler to cover its issue latency)
-template <int PASS> struct AttCfg {
+template <int PASS, bool TWO = false> struct AttCfg {
   static constexpr int kSoftmaxWarps = PASS == 1 ? 8 : 16;
   static constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
   // pass 2: warp 2 loads V on its own ring, so a K tile is never queued behind a V tile that waits for
   // a PV to retire (the K/V prefetch distance was what bounded the whole kernel); warp 3 idles so that
   // softmax warp w keeps TMEM lane quarter w & 3
   static constexpr int kFirstSoftmaxWarp = PASS == 1 ? 2 : 4;
-  static constexpr int kThreads = 32 * kFirstSoftmaxWarp + kSoftmaxThreads;
+  // TWO (ping-pong pass 2 of long self-attention): one more warp after the softmax warps -- the QK^T issuer of the
+  // SECOND query half.  (672 threads leave 80 registers per thread instead of 96: short key sequences and the MUFU-heavy
+  // uniform map lose more to that than the second issuer returns, so they keep one issuer.)  A role warp is one
+  // thread of serial code (~10 cycles per instruction: barrier polls, descriptor arithmetic, 64 cycles per MMA it
+  // feeds); issuing both halves' QK^T cost one warp ~4100 cycles per K tile against the ~1900 the softmax groups
+  // need (clock64 timeline of CTA 0, scripts/attn_trace.py) -- it, not any pipe, bounded pass 2
+  static constexpr int kQkWarpB = kFirstSoftmaxWarp + kSoftmaxWarps;
+  static constexpr int kThreads = 32 * kFirstSoftmaxWarp + kSoftmaxThreads + (TWO ? 32 : 0);
   static constexpr int kSplit = kSoftmaxWarps / 4;     // column splits of the 128-wide score tile
   static constexpr int kCh = 4 / kSplit;               // 32-column chunks per thread
 };
@@ -56,6 +64,7 @@ struct AttnDev {
   int nh;                       // 128-row query halves per work item (2: each K/V tile is loaded once for both)
   int nq_buf, nk_buf, nv_buf, no_buf;
   int ns;                       // S buffers in tensor memory (2, or 3 for the ping-pong pass 2 at dp = 64)
+  int ptm;                      // pass 2, ns == 3: P' stays in tensor memory (written over its own S tile) as the PV MMA's A operand
   float alpha;  // scale * log2(e)
   int map_mode, real_time, start_peak;
   const float* delta;
@@ -84,9 +93,14 @@ struct AttnDev {
 
 // barrier indices (rings of up to 4)
 constexpr int kRing = 4;
+// S-full / S-empty come in two sets of three (ping-pong pass 2 with three S buffers and one QK^T issuer per query half):
+// buffer sb is used by steps of BOTH halves in turn, and a waiter that sees only every second phase of a barrier
+// cannot tell "two phases ago" from "now" by parity -- so each (buffer, half) pair has its own barrier: S-full[sb + 3 g]
+// is committed by issuer g and awaited by softmax group g, S-empty[sb + 3 g] is awaited by issuer g and signalled by
+// whoever releases the tile to it (the other half's step three earlier).  Everything else uses set 0.
 enum { B_QFULL = 0, B_QEMPTY = B_QFULL + kRing, B_KFULL = B_QEMPTY + kRing, B_KEMPTY = B_KFULL + kRing,
-       B_VFULL = B_KEMPTY + kRing, B_VEMPTY = B_VFULL + kRing, B_SFULL = B_VEMPTY + kRing, B_SEMPTY = B_SFULL + 3,
-       B_PFULL = B_SEMPTY + 3, B_PEMPTY = B_PFULL + 2, B_OFULL = B_PEMPTY + 2, B_OEMPTY = B_OFULL + 2,
+       B_VFULL = B_KEMPTY + kRing, B_VEMPTY = B_VFULL + kRing, B_SFULL = B_VEMPTY + kRing, B_SEMPTY = B_SFULL + 6,
+       B_PFULL = B_SEMPTY + 6, B_PEMPTY = B_PFULL + 3, B_OFULL = B_PEMPTY + 2, B_OEMPTY = B_OFULL + 2,
        B_COUNT = B_OEMPTY + 2 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -180,11 +194,11 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
 // run half a step apart, so one group's TMEM-load / proxy-fence / barrier latencies and its whole O epilogue
 // are covered by the other group's ALU work (with all 16 warps in lock-step on one tile they were not:
 // 45 % issue utilisation, ncu profiles/r1e_attention.txt).
-template <int PASS, int MODE, bool CODES, bool PP>
-__global__ void __launch_bounds__(AttCfg<PASS>::kThreads, PASS == 1 ? 2 : 1)
+template <int PASS, int MODE, bool CODES, bool PP, bool TWO = false>
+__global__ void __launch_bounds__(AttCfg<PASS, TWO>::kThreads, PASS == 1 ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnDev p) {
-  using Cfg = AttCfg<PASS>;
+  using Cfg = AttCfg<PASS, TWO>;
   constexpr int kSoftmaxWarps = Cfg::kSoftmaxWarps, kSoftmaxThreads = Cfg::kSoftmaxThreads;
   constexpr int kSplit = PP ? 2 : Cfg::kSplit, kCh = PP ? 2 : Cfg::kCh;
   constexpr int kGroupThreads = PP ? kSoftmaxThreads / 2 : kSoftmaxThreads;   // threads sharing one score tile
@@ -214,9 +228,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     prefetch_tmap(&tm_k);
     if (PASS == 2) prefetch_tmap(&tm_v);
     for (int i = 0; i < B_COUNT; ++i) {
-      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 3) || (i >= B_PFULL && i < B_PFULL + 2) ||
+      // (P' in tensor memory: the S tile is released by the PV MMAs' commit, not by the softmax warps)
+      const bool all_sm = (i >= B_SEMPTY && i < B_SEMPTY + 6 && !(PASS == 2 && p.ptm)) || (i >= B_PFULL && i < B_PFULL + 3) ||
                           (i >= B_OEMPTY && i < B_OEMPTY + 2);
-      mbar_init(&bars[i], all_sm ? (PP ? kSoftmaxWarps / 2 : kSoftmaxWarps) : 1);
+      const bool k_two = TWO && i >= B_KEMPTY && i < B_KEMPTY + kRing;   // one commit per QK^T issuer
+      mbar_init(&bars[i], all_sm ? (PP ? kSoftmaxWarps / 2 : kSoftmaxWarps) : (k_two ? 2 : 1));
     }
     fence_barrier_init();
   }
@@ -307,6 +323,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_pv = [&](uint32_t u, uint32_t g, uint32_t on, bool first, bool last, bool lastq) {
         const uint32_t slot = g % nvb, pb = u & 1, ob = on % nob;
         mbar_wait(&bars[B_VFULL + slot], (g / nvb) & 1);
+        if (p.ptm) {
+          // P'(u) sits in tensor memory, written over the first 32 columns of each 64-column half of its own S tile:
+          // A operand straight from TMEM (8 packed columns per K = 16 step).  With P' in shared memory every
+          // M128 x N64 x K16 MMA read 6 KB of operands (48 cycles at the 128 B/clk shared-memory port, more than its
+          // 32 cycles of math) and the softmax warps wrote another 32 KB per step through the same port: the port,
+          // not the tensor pipe or the ALUs, bounded pass 2 (~170 KB per 128 x 128 step against 1885 cycles).
+          const uint32_t sb = u % ns;
+          mbar_wait(&bars[B_PFULL + sb], (u / ns) & 1);
+          if (first) mbar_wait(&bars[B_OEMPTY + ob], ((on / nob) & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t db0 = dv0 + slot * vstep;
+          const uint32_t d_o = tmem_o + ob * p.dp, a_t = tmem_base + sb * kTileK;
+          if (elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc_mma_f16_ts(d_o, a_t + c * 64 + ks * 8, db0 + c * vcstep + 2 * ks, idesc_o, (!first || (c | ks) != 0) ? 1u : 0u);
+            }
+            if (lastq) tc_commit(&bars[B_VEMPTY + slot]);
+            tc_commit(&bars[B_SEMPTY + sb + (TWO ? 3 * ((u & 1) ^ 1) : 0)]);   // the S / P' tile is free for the QK^T of step u + 3 (TWO: the other half's issuer)
+            if (last) tc_commit(&bars[B_OFULL + ob]);
+          }
+          __syncwarp();
+          return;
+        }
         mbar_wait(&bars[B_PFULL + pb], (u >> 1) & 1);
         if (first) mbar_wait(&bars[B_OEMPTY + ob], ((on / nob) & 1) ^ 1);   // the epilogue drained this accumulator
         tc_fence_after();
@@ -333,10 +375,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (TWO && warp == Cfg::kQkWarpB)) {
     // ------------------------------------------------------------------ QK^T issuer (warp-converged, one elected
-    // lane issues: see the PV issuer)
+    // lane issues: see the PV issuer).  Ping-pong pass 2: warp 1 issues for query half 0, warp kQkWarpB for half 1.
     {
+      constexpr bool two = TWO;
+      const uint32_t h_first = (two && warp != 1) ? 1u : 0u, h_step = two ? 2u : 1u;
       const uint32_t idesc_s = umma_idesc_f16(kTileQ, kTileK);
       const uint64_t dq0 = umma_desc_sw128(smem_u32(s_q)), dk0 = umma_desc_sw128(smem_u32(s_k));
       const uint32_t cstep = kChunkBytes >> 4, qstep = q_bytes >> 4;      // descriptor address field: 16-byte units
@@ -352,10 +396,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               mbar_wait(&bars[B_KFULL + gp % nkb], (gp / nkb) & 1);
             }
             const uint32_t slot0 = (g * kparts) % nkb, slot1 = (g * kparts + kparts - 1) % nkb;
-            for (uint32_t h = 0; h < nh; ++h) {
+            for (uint32_t h = h_first; h < nh; h += h_step) {
               const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu % ns;
               if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
-              mbar_wait(&bars[B_SEMPTY + sb], ((uu / ns) & 1) ^ 1);
+              const uint32_t sset = (two && ns == 3) ? 3 * h : 0;     // barrier set of this query half
+              if (two && ns == 3) {
+                if (uu >= 3) mbar_wait(&bars[B_SEMPTY + sb + sset], ((uu - 3) / 6) & 1);   // step uu - 3 released the tile
+              } else {
+                mbar_wait(&bars[B_SEMPTY + sb], ((uu / ns) & 1) ^ 1);
+              }
               tc_fence_after();
               const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot0 * qstep, db1 = dk0 + slot1 * qstep;
               const uint32_t d_s = tmem_base + sb * kTileK;
@@ -372,9 +421,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                       tc_mma_f16(d_s, da0 + c * cstep + 2 * ks, db1 + c * cstep + 2 * ks, idesc_s, 1u);
                   }
                 }
-                tc_commit(&bars[B_SFULL + sb]);
+                tc_commit(&bars[B_SFULL + sb + sset]);
                 if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);         // last read of this Q tile
-                if (h == nh - 1) {                                           // last read of this K tile
+                if (h == nh - 1 || two) {                                    // (this issuer's) last read of this K tile
                   tc_commit(&bars[B_KEMPTY + slot0]);
                   if (kparts == 2) tc_commit(&bars[B_KEMPTY + slot1]);
                 }
@@ -387,7 +436,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int part = 0; part < kparts; ++part) {
             const uint32_t gp = g * kparts + part, slot = gp % nkb;
             mbar_wait(&bars[B_KFULL + slot], (gp / nkb) & 1);
-            for (uint32_t h = 0; h < nh; ++h) {
+            for (uint32_t h = h_first; h < nh; h += h_step) {
               const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu % ns;
               if (part == 0) {
                 if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
@@ -406,7 +455,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                   tc_commit(&bars[B_SFULL + sb]);
                   if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);       // last read of this Q tile
                 }
-                if (h == nh - 1) tc_commit(&bars[B_KEMPTY + slot]);          // last read of this ring entry
+                if (h == nh - 1 || two) tc_commit(&bars[B_KEMPTY + slot]);   // (this issuer's) last read of this ring entry
               }
               __syncwarp();
             }
@@ -586,17 +635,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < p.nkv; ++j, ++u) {
           const uint32_t ph = u & 1;              // phase of the group's P' buffer
           const uint32_t uu = 2 * u + grp, sb = uu % ns;   // CTA-wide step number -> its S buffer
-          mbar_wait(&bars[B_SFULL + sb], (uu / ns) & 1);
+          if (TWO && ns == 3) mbar_wait(&bars[B_SFULL + sb + 3 * grp], (uu / 6) & 1);   // this half's own barrier set
+          else mbar_wait(&bars[B_SFULL + sb], (uu / ns) & 1);
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + lane_addr + sb * kTileK + col_lo + cc * 32, r);
             tc_wait_ld();
-            if (cc == 1) {                        // all of this thread's scores are in registers: free the S tile
+            if (cc == 1 && !p.ptm) {              // all of this thread's scores are in registers: free the S tile
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb]);
+              if (lane == 0) mbar_arrive(&bars[B_SEMPTY + sb + ((TWO && ns == 3) ? 3 * (grp ^ 1) : 0)]);   // to the next user's issuer
             }
             uint32_t h2[16];
             map_chunk<MODE, CODES>(r, h2, alpha, gamma, qcap, p.qmax, j * kTileK + col_lo + cc * 32, s_len, code_row);
@@ -605,11 +655,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 p0 = ex2_approx(fmaf(alpha, __uint_as_float(r[0]), -beta));
                 h2[0] &= 0xFFFF0000u;             // column 0 leaves the MMA; added back in the epilogue
               }
-              mbar_wait(&bars[B_PEMPTY + pbuf], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
+              if (!p.ptm) mbar_wait(&bars[B_PEMPTY + pbuf], ph ^ 1);   // the PV of the previous K tile has consumed this P' buffer
+            }
+            if (p.ptm) {
+              // 32 fp16 = 16 packed words over the scores they came from: columns [col_lo + 16 cc, + 16) of the row
+              // (this thread's own, already consumed, quarter of the S tile)
+              tmem_st_32x16(tmem_base + lane_addr + sb * kTileK + col_lo + cc * 16, h2);
+              continue;
             }
 #pragma unroll
             for (int v = 0; v < 4; ++v)
               st_shared_v4(sub + sw128_offset(row, cc * 4 + v), h2[4 * v], h2[4 * v + 1], h2[4 * v + 2], h2[4 * v + 3]);
+          }
+          if (p.ptm) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
+            continue;
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -859,6 +922,12 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   }
   p.no_buf = a->dp <= 128 ? 2 : 1;
   p.ns = (p.nh == 2 && a->dp <= 64) ? 3 : 2;
+  static int ptm_on = -1;       // DGQ_ATTN_PTMEM=0: P' through shared memory everywhere (A/B runs)
+  if (ptm_on < 0) {
+    const char* env = getenv("DGQ_ATTN_PTMEM");
+    ptm_on = (env == nullptr || atoi(env) != 0) ? 1 : 0;
+  }
+  p.ptm = (ptm_on && p.ns == 3) ? 1 : 0;
   p.items = a->b * a->heads * ((p.q_tiles + p.nh - 1) / p.nh);
   p.alpha = a->scale * 1.4426950408889634f;
   p.map_mode = a->map_mode; p.real_time = a->real_time; p.start_peak = a->start_peak;
@@ -884,6 +953,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   AttnDev p1 = p;                       // pass 1 keeps two CTAs per SM: a smaller Q ring, 256 TMEM columns
   if (p1.nq_buf > 2) p1.nq_buf = 2;
   p1.ns = 2;
+  p1.ptm = 0;
   const uint32_t smem1 = q_bytes * (p1.nq_buf + p1.nk_buf) + tail;
   const uint32_t smem2 = q_bytes * (p.nq_buf + p.nk_buf) + p.nv_buf * 2 * a->dp * 128 + 4 * kChunkBytes + tail;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnDev);
@@ -891,10 +961,18 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   KernelFn k2;
   const bool cd = a->codes != nullptr;
   const bool pp = p.nh == 2;            // two query halves per item: one softmax warp group per half
+  // a second QK^T issuer for long self-attention with the log2 map (DGQ_ATTN_TWO=0 switches it off: A/B runs)
+  static int two_on = -1;
+  if (two_on < 0) {
+    const char* env = getenv("DGQ_ATTN_TWO");
+    two_on = (env == nullptr || atoi(env) != 0) ? 1 : 0;
+  }
+  const bool two = two_on && pp && !cd && a->map_mode == DGQ_MAP_LOG2 && p.nkv >= 4;
   switch (a->map_mode) {
     case DGQ_MAP_LOG2:
       k2 = cd ? (pp ? attention_kernel<2, DGQ_MAP_LOG2, true, true> : attention_kernel<2, DGQ_MAP_LOG2, true, false>)
-              : (pp ? attention_kernel<2, DGQ_MAP_LOG2, false, true> : attention_kernel<2, DGQ_MAP_LOG2, false, false>);
+              : (pp ? (two ? attention_kernel<2, DGQ_MAP_LOG2, false, true, true> : attention_kernel<2, DGQ_MAP_LOG2, false, true>)
+                    : attention_kernel<2, DGQ_MAP_LOG2, false, false>);
       break;
     case DGQ_MAP_UNIFORM:
       k2 = cd ? (pp ? attention_kernel<2, DGQ_MAP_UNIFORM, true, true> : attention_kernel<2, DGQ_MAP_UNIFORM, true, false>)
@@ -911,6 +989,7 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
     KernelFn all[] = {attention_kernel<1, 0, false, false>,
                       attention_kernel<2, DGQ_MAP_LOG2, true, false>, attention_kernel<2, DGQ_MAP_LOG2, true, true>,
                       attention_kernel<2, DGQ_MAP_LOG2, false, false>, attention_kernel<2, DGQ_MAP_LOG2, false, true>,
+                      attention_kernel<2, DGQ_MAP_LOG2, false, true, true>,
                       attention_kernel<2, DGQ_MAP_UNIFORM, true, false>, attention_kernel<2, DGQ_MAP_UNIFORM, true, true>,
                       attention_kernel<2, DGQ_MAP_UNIFORM, false, false>, attention_kernel<2, DGQ_MAP_UNIFORM, false, true>,
                       attention_kernel<2, DGQ_MAP_NONE, false, false>, attention_kernel<2, DGQ_MAP_NONE, false, true>};
@@ -930,6 +1009,6 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   k1<<<grid1, AttCfg<1>::kThreads, smem1, s>>>(tq, tk, tv, p1);
-  k2<<<grid2, AttCfg<2>::kThreads, smem2, s>>>(tq, tk, tv, p);
+  k2<<<grid2, two ? AttCfg<2, true>::kThreads : AttCfg<2>::kThreads, smem2, s>>>(tq, tk, tv, p);
   DGQ_RETURN_LAST_ERROR();
 }
