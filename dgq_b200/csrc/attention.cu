@@ -31,6 +31,13 @@
 #include "ptx.cuh"
 
 namespace dgq {
+// role timeline for scripts/attn_trace.py (-DDGQ_ATTN_TRACE builds only): SM clock of CTA 0's role events per step
+#ifdef DGQ_ATTN_TRACE
+__device__ long long g_trace[8][512];
+#define DGQ_TR(role, idx) do { if (PASS == 2 && blockIdx.x == 0 && static_cast<uint32_t>(idx) < 512u) g_trace[role][idx] = clock64(); } while (0)
+#else
+#define DGQ_TR(role, idx) do { } while (0)
+#endif
 
 
 // warp 0 loader, warp 1 MMA, then the softmax warps: 8 in pass 1 (thread = row x 64-column half; the pass
@@ -336,6 +343,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           const uint64_t db0 = dv0 + slot * vstep;
           const uint32_t d_o = tmem_o + ob * p.dp, a_t = tmem_base + sb * kTileK;
           if (elect_one()) {
+            DGQ_TR(3, u);                                             // PV of step u goes out
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
@@ -398,6 +406,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const uint32_t slot0 = (g * kparts) % nkb, slot1 = (g * kparts + kparts - 1) % nkb;
             for (uint32_t h = h_first; h < nh; h += h_step) {
               const uint32_t uu = u + h, qn = it * nh + h, qb = qn % nqb, sb = uu % ns;
+              if (elect_one()) DGQ_TR(0, uu);                         // issuer reaches the step
               if (j == 0) mbar_wait(&bars[B_QFULL + qb], (qn / nqb) & 1);
               const uint32_t sset = (two && ns == 3) ? 3 * h : 0;     // barrier set of this query half
               if (two && ns == 3) {
@@ -409,6 +418,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
               const uint64_t da0 = dq0 + qb * qstep, db0 = dk0 + slot0 * qstep, db1 = dk0 + slot1 * qstep;
               const uint32_t d_s = tmem_base + sb * kTileK;
               if (elect_one()) {
+                DGQ_TR(1, uu);                                        // waits done: first MMA goes out
                 for (int c = 0; c < dchunks; ++c) {
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
@@ -422,6 +432,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                   }
                 }
                 tc_commit(&bars[B_SFULL + sb + sset]);
+                DGQ_TR(2, uu);                                        // S-full commit issued
                 if (j == p.nkv - 1) tc_commit(&bars[B_QEMPTY + qb]);         // last read of this Q tile
                 if (h == nh - 1 || two) {                                    // (this issuer's) last read of this K tile
                   tc_commit(&bars[B_KEMPTY + slot0]);
@@ -635,8 +646,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < p.nkv; ++j, ++u) {
           const uint32_t ph = u & 1;              // phase of the group's P' buffer
           const uint32_t uu = 2 * u + grp, sb = uu % ns;   // CTA-wide step number -> its S buffer
+          if (etid == 0) DGQ_TR(4, uu);                               // group asks for S(uu)
           if (TWO && ns == 3) mbar_wait(&bars[B_SFULL + sb + 3 * grp], (uu / 6) & 1);   // this half's own barrier set
           else mbar_wait(&bars[B_SFULL + sb], (uu / ns) & 1);
+          if (etid == 0) DGQ_TR(5, uu);                               // ... has it
           tc_fence_after();
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -672,6 +685,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars[B_PFULL + sb]);
+            if (etid == 0) DGQ_TR(6, uu);                             // P'(uu) published
             continue;
           }
           fence_proxy_async_smem();
@@ -1012,3 +1026,9 @@ extern "C" int dgq_attention(const dgq_attn_t* a, void* stream) {
   k2<<<grid2, two ? AttCfg<2, true>::kThreads : AttCfg<2>::kThreads, smem2, s>>>(tq, tk, tv, p);
   DGQ_RETURN_LAST_ERROR();
 }
+
+#ifdef DGQ_ATTN_TRACE
+extern "C" int dgq_attn_trace_dump(long long* host) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host, dgq::g_trace, sizeof(dgq::g_trace)));
+}
+#endif

@@ -1,13 +1,32 @@
-"""Timeline of the pass-2 attention roles on CTA 0 (needs the tracing build of attention.cu: see DESIGN.md 4.2):
-per score-tile step, the SM clock at which the QK^T issuer issued / committed, the PV issuer issued / committed and the
-softmax group began waiting for S, got S, released S, waited for / got the P' buffer and published P'."""
+"""Timeline of the pass-2 attention roles on CTA 0: the SM clock at which, per score-tile step, the
+QK^T issuer reached the step / sent its first MMA / issued the S-full commit, the PV issuer sent P'V, and the softmax
+group asked for S, got it and published P'.  Needs the tracing build of attention.cu:
+
+    python scripts/attn_trace.py --build          # here (nvcc): dgq_b200/_C/libdgq_b200_trace.so, -DDGQ_ATTN_TRACE
+    python scripts/attn_trace.py [shape index]    # on the GPU box (shapes of scripts/attn_bench.py)
+"""
 import ctypes as C
 import os
+import subprocess
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import dgq_b200._lib as L  # noqa: E402
-L.LIB_PATH = os.path.join(os.path.dirname(L.LIB_PATH), "libdgq_b200_trace.so")
+from dgq_b200 import build as B  # noqa: E402
+
+TRACE_LIB = os.path.join(B.OUT_DIR, "libdgq_b200_trace.so")
+
+if "--build" in sys.argv:
+    B.build()
+    obj = os.path.join(B.OUT_DIR, "attention_trace.o")
+    subprocess.run(["nvcc"] + [f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DDGQ_ATTN_TRACE", "-c", os.path.join(B.CSRC, "attention.cu"), "-o", obj], check=True)
+    objs = [os.path.join(B.OUT_DIR, s.replace(".cu", ".o")) for s in B.SOURCES if s != "attention.cu"] + [obj]
+    subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", TRACE_LIB] + objs, check=True)
+    print(TRACE_LIB)
+    sys.exit(0)
+
+L.LIB_PATH = TRACE_LIB
 import torch  # noqa: E402
 from dgq_b200 import engine, ops  # noqa: E402
 from scripts.attn_bench import SHAPES, qparam  # noqa: E402
@@ -34,8 +53,20 @@ lib = L.lib()
 lib.dgq_attn_trace_dump.argtypes = [C.c_void_p]
 assert lib.dgq_attn_trace_dump(buf) == 0
 tr = [[buf[r * 512 + i] for i in range(512)] for r in range(8)]
-t0 = tr[2][0]
-print(label, "QK issuer, per step uu: loop top | after S-empty wait | MMAs issued | S-full commit issued | all commits issued | after syncwarp   (K tile g = uu // 2: asks | has)")
-for uu in range(8, 40):
-    g_ = uu // 2
-    print(f"{uu:4d} | {tr[6][uu]-t0:8d} {tr[2][uu]-t0:8d} {tr[3][uu]-t0:8d} {tr[4][uu]-t0:8d} {tr[5][uu]-t0:8d} {tr[7][uu]-t0:8d}   | K {tr[0][g_]-t0:8d} {tr[1][g_]-t0:8d}")
+names = ["qk_reach", "qk_mma", "qk_commit", "pv_mma", "sm_ask_s", "sm_got_s", "sm_pub_p"]
+t0 = tr[1][0]
+print(label, "| step |", " ".join(f"{n:>10s}" for n in names))
+for u in range(8, 32):
+    print(f"{u:4d} |", " ".join(f"{tr[r][u] - t0:10d}" for r in range(7)))
+
+
+def avg(f, lo=8, hi=56):
+    xs = [f(u) for u in range(lo, hi)]
+    return sum(xs) / len(xs)
+
+
+print("cycles per step (same half, u -> u + 2, halved):", avg(lambda u: tr[6][u + 2] - tr[6][u]) / 2)
+print("QK^T issuer of a half, per own step: reach -> first MMA", avg(lambda u: tr[1][u] - tr[0][u]), "| MMAs + commit", avg(lambda u: tr[2][u] - tr[1][u]),
+      "| commit -> reaches its next step", avg(lambda u: tr[0][u + 2] - tr[2][u]))
+print("softmax half: waits for S", avg(lambda u: tr[5][u] - tr[4][u]), "| S -> P' published", avg(lambda u: tr[6][u] - tr[5][u]),
+      "| P' published -> PV issued", avg(lambda u: tr[3][u] - tr[6][u]))
