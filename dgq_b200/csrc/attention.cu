@@ -154,6 +154,20 @@ __device__ __forceinline__ void map_chunk(const uint32_t (&r)[32], uint32_t (&h2
   // output -- computed by the direct formula -- did not even show.)
   const float q_inv = __frcp_rn(qcap);
   const float a_sat = -alpha * q_inv, g_sat = gamma * q_inv;   // loop-invariant: hoisted by the compiler
+  if (MODE == DGQ_MAP_LOG2 && !CODES && qmax >= qcap) {
+    // the hot case as straight-line code (the level test inside the unrolled loop compiled to a branch per pair)
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float y0, y1;
+      asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y0) : "f"(__uint_as_float(r[i])), "f"(a_sat), "f"(g_sat));
+      asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y1) : "f"(__uint_as_float(r[i + 1])), "f"(a_sat), "f"(g_sat));
+      const uint32_t b0 = __float_as_uint(fmaf(y0, qcap, 12582912.0f)), b1 = __float_as_uint(fmaf(y1, qcap, 12582912.0f));
+      const __half2 hh = __floats2half2_rn(__uint_as_float(b0 * 0xFF800000u + 0x3F800000u),
+                                           __uint_as_float(b1 * 0xFF800000u + 0x3F800000u));
+      h2[i >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     float pv[2];
