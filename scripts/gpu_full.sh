@@ -19,9 +19,18 @@ ncu -i gpurun_out/r2_gemm_final.ncu-rep --page raw --csv \
   > gpurun_out/r2_gemm_final_dram.csv 2>&1
 cat gpurun_out/r2_gemm_final_dram.csv | cut -c1-600
 python scripts/make_gemm_traffic.py gpurun_out/r2_gemm_final_dram.csv gpurun_out/r2_gemm_traffic.json
+cp gpurun_out/r2_gemm_traffic.json profiles/r2_gemm_traffic.json   # the bench lines below carry this same-build figure
 echo "== bench default (config 4, CPU legs)"
 timeout 1200 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 tail -c 600 gpurun_out/r2_bench_default.json
 echo "== bench --impl reference"
 timeout 900 python bench.py --impl reference > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err
 tail -c 800 gpurun_out/r2_bench_reference.json
+echo "== bench lines of the other BASELINE configs"
+for c in 1 2 3 5; do
+  timeout 900 python bench.py --config $c --no-cpu > gpurun_out/r2_bench_c$c.json 2> gpurun_out/r2_bench_c$c.err
+  tail -c 300 gpurun_out/r2_bench_c$c.json; echo
+done
+echo "== kernel benches"
+timeout 200 python scripts/attn_bench.py 2>&1 | tail -7
+timeout 300 python scripts/gemm_i8_bench.py > gpurun_out/gemm_i8_bench.log 2>&1; tail -3 gpurun_out/gemm_i8_bench.log | cut -c1-300
