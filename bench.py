@@ -683,11 +683,27 @@ def torch_eager_b200(torch, cfg, qnn, dev):
                 oracle_call(torch, cfg, state, inp)
                 torch.cuda.synchronize()
                 times.append(time.perf_counter() - t0)
+        # the reference's --fp16 arm (src/inference_qmodel.py:95-98, qnn.half()): the same eager graph with its matmuls /
+        # convs in fp16 (autocast); a throughput figure only -- half-precision fake quantisation is not a parity target
+        fp16 = None
+        try:
+            t16 = []
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                for _ in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    oracle_call(torch, cfg, state, inp)
+                    torch.cuda.synchronize()
+                    t16.append(time.perf_counter() - t0)
+            fp16 = {"value": round(1.0 / min(t16[1:]), 4), "unit": "UNet calls/s at batch 1", "ms_per_call": round(min(t16[1:]) * 1e3, 1)}
+        except Exception as e:
+            fp16 = {"unavailable": f"{type(e).__name__}: {e}"[:160]}
         del state
         torch.cuda.empty_cache()
         best = min(times[1:])
         return {"value": round(1.0 / best, 4), "unit": "UNet calls/s at batch 1", "kind": "port, torch eager fp32 on the same B200",
-                "sample": f"batch 1 (one {cfg['model'].upper()} UNet call), best of 2 after 1 warm-up, {best * 1e3:.0f} ms/call"}
+                "sample": f"batch 1 (one {cfg['model'].upper()} UNet call), best of 2 after 1 warm-up, {best * 1e3:.0f} ms/call",
+                "fp16_autocast": fp16}
     except Exception as e:   # a baseline must never take the bench down
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 

@@ -21,10 +21,15 @@
 // O accumulators all carry over from item to item, so the QK^T of the next item overlaps the softmax / PV /
 // epilogue of the current one (cross-attention, S = 77, is a single K tile per item: without this it is launch-
 // and latency-bound).
-// Roles: warp 0 Q/K TMA loader | warp 1 QK^T issuer (one lane) | pass 2: warp 2 V loader, warp 3 PV issuer |
-//        softmax warps (8 in pass 1, 16 in pass 2; TMEM lane == row, so row reductions need no shuffles).
-// TMEM: S 2 x 128 columns + O 1-2 x dp columns.  P' goes through smem in the UMMA K-major 128B-swizzle
-// layout, written by the softmax threads.
+// Roles: warp 0 Q/K TMA loader | warp 1 QK^T issuer | pass 2: warp 2 V loader, warp 3 PV issuer |
+//        softmax warps (8 in pass 1, 16 in pass 2; TMEM lane == row, so row reductions need no shuffles) |
+//        long log2 self-attention (template TWO): one more warp, the QK^T issuer of the second query half.
+//        Role warps run warp-converged (all lanes loop, one elected lane issues).
+// TMEM: S 2-3 x 128 columns + O 1-2 x dp columns.  P' goes through smem in the UMMA K-major 128B-swizzle
+// layout, written by the softmax threads -- or, with three S buffers (dp = 64), stays in tensor memory, written
+// over its own score columns, as the PV MMA's A operand (ptm).
+// Operands (round 2): Q = bare integers (code - zp), K = every scale folded in, as an fp16 hi | lo pair (two QK^T
+// MMAs per tile): S is exact to fp32 rounding, see DESIGN.md 4.2.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -47,8 +52,8 @@ template <int PASS, bool TWO = false> struct AttCfg {
   static constexpr int kSoftmaxWarps = PASS == 1 ? 8 : 16;
   static constexpr int kSoftmaxThreads = 32 * kSoftmaxWarps;
   // pass 2: warp 2 loads V on its own ring, so a K tile is never queued behind a V tile that waits for
-  // a PV to retire (the K/V prefetch distance was what bounded the whole kernel); warp 3 idles so that
-  // softmax warp w keeps TMEM lane quarter w & 3
+  // a PV to retire (the K/V prefetch distance was what bounded the whole kernel); warp 3 issues the PV MMAs;
+  // four role warps keep softmax warp w on TMEM lane quarter w & 3
   static constexpr int kFirstSoftmaxWarp = PASS == 1 ? 2 : 4;
   // TWO (ping-pong pass 2 of long self-attention): one more warp after the softmax warps -- the QK^T issuer of the
   // SECOND query half.  (672 threads leave 80 registers per thread instead of 96: short key sequences and the MUFU-heavy
