@@ -656,6 +656,19 @@ __global__ void __launch_bounds__(kLnThreads, 2) ln_tile_kernel(const TIn* __res
         uaq_lean_lh<false, 8>(t, d, inv, qlo, qhi);
         *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * c) = pack8(t);
       }
+    } else if (q.mode == DGQ_Q_SCALAR) {
+      // per-tensor scale (every layer of the g = 1 configs): the triple and the clamp bounds once per quantizer, not
+      // once per row (the generic path below re-read them through L1 for each row, with a division when q.inv is absent)
+      const float dd = __ldg(q.delta), zz = __ldg(q.zp);
+      const float ii = q.inv != nullptr ? __ldg(q.inv) : rcp_rn_slow(dd);
+      const float lo = -zz, hi = __fsub_rn(q.qmax, zz);
+      for (int r = r_begin; r < r_end; ++r) {
+        const float4 a0 = tile4[(r * 2 + 0) * cvec + cv], a1 = tile4[(r * 2 + 1) * cvec + cv];
+        float t[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (q.emit_int) uaq_lean1_lh<true, 8>(t, dd, ii, lo, hi);
+        else uaq_lean1_lh<false, 8>(t, dd, ii, lo, hi);
+        store8(rq.out[o], static_cast<size_t>(row0 + r) * c + k0, t, q.emit_int, zz);
+      }
     } else {
       for (int r = r_begin; r < r_end; ++r) {
         const float4 a0 = tile4[(r * 2 + 0) * cvec + cv], a1 = tile4[(r * 2 + 1) * cvec + cv];
