@@ -147,6 +147,20 @@ def test_attention_modes(mode, shape):
     assert_close_mod_flips(out, ref, 2e-3 if mode == "none" else None)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", ["log_rt", "uniform"])
+@pytest.mark.parametrize("shape", [(6, 10, 1024, 1024, 64),     # 240 items on 148 CTAs, 8 K tiles: the two-issuer log2 kernel
+                                   (8, 8, 512, 512, 80),        # dp = 128 ping-pong kernel, 256 items
+                                   (170, 1, 128, 256, 160),     # dp = 192 (one query half per item), 170 items
+                                   (40, 4, 256, 77, 64)])       # cross-attention, 160 single-tile items
+def test_attention_persistent_multi_item(mode, shape):
+    """every CTA walks SEVERAL work items as one pipeline (rings, S / P' buffers and O accumulators carry over):
+    the barrier phases of the role warps must survive the item boundary -- a hang here is a test failure (timeout)"""
+    b, heads, t, s, d = shape
+    out, ref, _ = run_case(b, heads, t, s, d, mode, s == 77, "d", seed=11)
+    assert_close_mod_flips(out, ref, None)
+
+
 @pytest.mark.parametrize("scales", ["d", "t", "scalar"])
 @pytest.mark.parametrize("mode", ["log_rt", "uniform"])
 def test_attention_start_peak(mode, scales):
