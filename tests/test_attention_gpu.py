@@ -151,6 +151,7 @@ def test_attention_modes(mode, shape):
 @pytest.mark.parametrize("mode", ["log_rt", "uniform"])
 @pytest.mark.parametrize("shape", [(6, 10, 1024, 1024, 64),     # 240 items on 148 CTAs, 8 K tiles: the two-issuer log2 kernel
                                    (8, 8, 512, 512, 80),        # dp = 128 ping-pong kernel, 256 items
+                                   (16, 8, 1024, 1024, 80),     # ... at the SD 32x32 size: 512 items, 8 K tiles
                                    (170, 1, 128, 256, 160),     # dp = 192 (one query half per item), 170 items
                                    (40, 4, 256, 77, 64)])       # cross-attention, 160 single-tile items
 def test_attention_persistent_multi_item(mode, shape):
