@@ -19,7 +19,7 @@ def gp(g, n, view, scale=1.0):
     return d[lab].view(view), z[lab].view(view)
 
 
-def run_case(b, heads, t, s, d, mode, start_peak, qk_scales, seed=0):
+def run_case(b, heads, t, s, d, mode, start_peak, qk_scales, seed=0, want_codes=True):
     from dgq_b200 import ops
     g = torch.Generator().manual_seed(seed)
     q = torch.randn(b, t, heads * d, generator=g).half()
@@ -70,12 +70,13 @@ def run_case(b, heads, t, s, d, mode, start_peak, qk_scales, seed=0):
     mm = {"none": ops.MAP_NONE, "uniform": ops.MAP_UNIFORM, "log_static": ops.MAP_LOG2, "log_rt": ops.MAP_LOG2}[mode]
     delta = act.get(f"{name}.aqtizer_w.delta")
     flat = lambda x, n: x.to(DEV).reshape(b * n, heads * d)   # noqa: E731
-    out, rt, codes = engine.attention_from_projections(
+    res = engine.attention_from_projections(
         flat(q, t), flat(k, s), flat(v, s), b, t, s, heads, d, qp("q", t), qp("k", s), qp("v", s),
         start_peak=start_peak, map_mode=mm, real_time=mode == "log_rt",
-        delta=delta.reshape(1).to(DEV) if delta is not None else None, want_codes=True)
+        delta=delta.reshape(1).to(DEV) if delta is not None else None, want_codes=want_codes)
+    out, rt, codes = res if want_codes else (res[0], res[1], None)
     out = out.view(b, t, heads * d).cpu().float()
-    if mode != "none":
+    if mode != "none" and want_codes:
         exact = engine.attn_plan(qp("q", t), dp)["split"]       # integer Q . (hi | lo) K: scores to ~22 bits
         check_codes(codes.cpu(), heads_first(q), heads_first(k), act, name, cfg, mode, start_peak, exact)
     return out, ref, rt
@@ -160,6 +161,9 @@ def test_attention_persistent_multi_item(mode, shape):
     b, heads, t, s, d = shape
     out, ref, _ = run_case(b, heads, t, s, d, mode, s == 77, "d", seed=11)
     assert_close_mod_flips(out, ref, None)
+    # ... and the production instantiations (no code output: the two-issuer kernel for long log2 self-attention)
+    out2, _, _ = run_case(b, heads, t, s, d, mode, s == 77, "d", seed=11, want_codes=False)
+    assert torch.equal(out2, out)
 
 
 @pytest.mark.parametrize("scales", ["d", "t", "scalar"])
