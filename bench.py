@@ -223,7 +223,7 @@ def run_cuda(args):
                    "act_dtype_between_kernels": str(ops.ACT_DTYPE).replace("torch.", ""), "cuda_graph": cfg["model"] != "layer",
                    "gemm_kinds": "kind::i8 (u8 x s8) for scalar / row-wise activation scales, kind::f16 for K-wise group scales"},
         "e2e": {"value": round(e2e_val, 3), "unit": cfg["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches_per_step * (args.steps + warmup), "launches_per_step": launches_per_step,
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,   # inside the timed region
         "clocks": sampler.summary(),
     }
     line.update(rooflines(cfg, breakdown, pk, pk_src))
